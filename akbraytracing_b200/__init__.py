@@ -1,0 +1,12 @@
+"""akbraytracing_b200 -- B200-native (sm_100a) drop-in for the two data-parallel hot paths of
+Kakekakechan/AKBRaytracing: the Huygens-Fresnel pair sum (wavecalc) and the ray / quadric-mirror
+chain (raytrace).  Hand-written CUDA behind a C-ABI (include/akb_b200.h); no CPU fallback."""
+from . import _lib
+from .wavecalc import (PHASE_EXACT, PHASE_FAITHFUL, WaveField3D, forward_propagation_cupy_batch,
+                       forward_propagation_cupy_batch_multi_gpu, forward_propagation_numpy_batch,
+                       fresnel_sum, fresnel_sum_sharded)
+from .raytrace import (PlanePoints, ell, intersect_reflect, mirr_ray_intersection, norm_vector,
+                       normalize_vector, plane_ray_intersection, reflect_ray, trace_chain)
+from .handoff import calc_dS, opl_to_field
+
+__version__ = "0.1.0"

@@ -355,8 +355,11 @@ def main():
         files[f"chain_{kind}_ref"] = {}
         gen_chain(files[f"chain_{kind}_ref"], geo, kind)
     files["geometry"] = geo
+    pkg_data = os.path.join(os.path.dirname(os.path.dirname(HERE)), "akbraytracing_b200", "data")
+    os.makedirs(pkg_data, exist_ok=True)
     for name, d in files.items():
-        path = os.path.join(HERE, name + ".npz")
+        # geometry.npz ships with the package (bench / workload builders read it on the GPU box)
+        path = os.path.join(pkg_data if name == "geometry" else HERE, name + ".npz")
         np.savez_compressed(path, **{k.replace("/", "__"): v for k, v in d.items()})
         print("wrote", path, os.path.getsize(path), "bytes")
 
