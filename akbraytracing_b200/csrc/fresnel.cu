@@ -7,35 +7,41 @@
 //   * a small pack kernel fuses u*ds (CPU0402:102 / K6), pads the source set to whole tiles and
 //     lays it out tile-contiguous [tile][sx|sy|sz|w_re|w_im][TILE] so that one TMA bulk copy
 //     (cp.async.bulk -> SASS UBLKCP) brings a tile into shared memory;
-//   * the pair kernel keeps DPT detector points + their complex accumulators in registers,
-//     streams source tiles through a 3-stage mbarrier ring and evaluates every pair with
-//     ~41 FP64-pipe instructions (no libdevice sincos: exact Cody-Waite reduction of k*r);
-//   * bound: FP64 ALU (DFMA pipe).  HBM traffic is 40 B per source per detector-block, i.e.
-//     ~0 B per pair; there is no dense contraction, so no tensor cores.
+//   * the pair kernel keeps DPT detector points + their complex accumulators in registers and
+//     streams source tiles through an mbarrier ring;
+//   * per pair: r = sqrt(dx^2+dy^2+dz^2) from one MUFU.RSQ64H + 7 FP64 ops (correctly rounded,
+//     also yields 1/(2r)), the phase k*r reduced EXACTLY (Cody-Waite with FMA) to a multiple of
+//     2*pi/512 plus a remainder |f| <= pi/512, exp(-i f) from a 2-term polynomial, and the
+//     multiple looked up in a 512-entry (cos, sin) table in shared memory: 36 FP64-pipe
+//     instructions and ~8 others per pair, no libdevice sincos (its Payne-Hanek slow path is
+//     unusable at k*r ~ 1e9);
+//   * bound: FP64 ALU (DFMA pipe, 64 lanes/SM).  HBM traffic is 40 B per source per
+//     detector block, i.e. ~0 B per pair; there is no dense contraction, so no tensor cores.
+#include <stdlib.h>
+
 #include "akb_common.cuh"
 
 namespace {
 
 using namespace akb;
 
-constexpr int TILE = 512;                    // source points per shared-memory stage
-constexpr int ROWS = 5;                      // sx, sy, sz, w_re, w_im
-constexpr int TILE_DOUBLES = ROWS * TILE;
-constexpr int TILE_BYTES = TILE_DOUBLES * 8; // 20 KiB
-constexpr int STAGES = 3;
+constexpr int ROWS = 5; // sx, sy, sz, w_re, w_im
 constexpr int THREADS = 256;
-constexpr int SMEM_BYTES = STAGES * TILE_BYTES + STAGES * 8;
 
 struct PhaseConst {
-    double k;    // FAITHFUL: phase = fl(k * r)
-    double q_hi; // EXACT: quarter turns per metre, k*(2/pi) = q_hi + q_lo
+    double k;        // FAITHFUL: phase = fl(k * r)
+    double inv_u;    // 1/u, u = 2*pi/TBL = reduction unit = angular step of the table
+    double neg_u_hi; // -u as hi + lo
+    double neg_u_lo;
+    double u;        // EXACT: remainder in units -> radians
+    double q_hi;     // EXACT: units per metre, k/u = q_hi + q_lo
     double q_lo;
 };
 
 // ---------------------------------------------------------------- pack
 __global__ void pack_sources_kernel(const double *__restrict__ sx, const double *__restrict__ sy,
                                     const double *__restrict__ sz, const double *__restrict__ u,
-                                    const double *__restrict__ ds, long long N, long long padded,
+                                    const double *__restrict__ ds, long long N, long long padded, int tile,
                                     double *__restrict__ packed)
 {
     long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -49,14 +55,14 @@ __global__ void pack_sources_kernel(const double *__restrict__ sx, const double 
         wr = mul(2.0, mul(u[2 * j], d));
         wi = mul(2.0, mul(u[2 * j + 1], d));
     }
-    long long tile = j / TILE;
-    int o = (int)(j % TILE);
-    double *t = packed + tile * TILE_DOUBLES;
-    t[0 * TILE + o] = sx[jj];
-    t[1 * TILE + o] = sy[jj];
-    t[2 * TILE + o] = sz[jj];
-    t[3 * TILE + o] = wr;
-    t[4 * TILE + o] = wi;
+    long long t_idx = j / tile;
+    int o = (int)(j % tile);
+    double *t = packed + t_idx * (long long)(ROWS * tile);
+    t[0 * tile + o] = sx[jj];
+    t[1 * tile + o] = sy[jj];
+    t[2 * tile + o] = sz[jj];
+    t[3 * tile + o] = wr;
+    t[4 * tile + o] = wi;
 }
 
 // ---------------------------------------------------------------- mbarrier / TMA bulk helpers
@@ -92,55 +98,143 @@ __device__ __forceinline__ void tma_bulk_load(uint32_t dst, const void *src, uin
                  : "memory");
 }
 
-// ---------------------------------------------------------------- one (detector, source) pair
+// ---------------------------------------------------------------- constants
+// FP64 constants live in constant memory so that they reach the DFMA as a c[bank][offset] /
+// uniform-register operand: as literals ptxas re-materialises each of them with two UMOVs per
+// loop iteration (30 extra issue slots per 4 pairs in the first version of this kernel).
+enum { KC_MAGIC, KC_NEG_MAGIC, KC_T1, KC_T2, KC_TC1, KC_COUNT };
+__constant__ double KC[KC_COUNT] = {
+    AKB_RND_MAGIC, -AKB_RND_MAGIC,
+    -1.0 / 6.0, 1.0 / 120.0, // sin f = f (1 + z (T1 + z T2)),  |f| <= pi/512: next term 1e-17 relative
+    1.0 / 24.0};             // cos f = 1 + z (-1/2 + z TC1),              next term 8e-17
+
+// ---------------------------------------------------------------- one (detector, source) pair, in three phases
+//
+// Cost model (measured on B200, tools/ubench/fp64_*.cu): the FP64 pipe takes one warp instruction
+// every 2 cycles per SM sub-partition, but 3 cycles when the instruction reads THREE distinct
+// 64-bit vector registers that the operand-reuse cache does not supply.  Constants (c[], uniform
+// registers, immediates) are free.  Hence: polynomials are closed with the constant 1.0, the
+// amplitude is applied by plain multiplications, and accumulations are ordered so that consecutive
+// instructions share an operand.  Per pair (FAITHFUL): 36 FP64 instructions, 5 of them 3-read.
+//
+// The 2*DPT pairs of one loop iteration go through the phases together, which puts the table load
+// of a pair ~40 FP64 instructions ahead of its use.
+struct PairA {
+    double p; // FAITHFUL: fl(k*r); EXACT: r
+    double h; // 1/(2r)
+    double t; // MAGIC + rint(phase / u); its low word is the table index
+};
+
 template <int MODE>
-__device__ __forceinline__ void accumulate_pair(double X, double Y, double Z, double sx, double sy, double sz,
-                                                double wr, double wi, const PhaseConst &pc, double &acc_re,
-                                                double &acc_im)
+__device__ __forceinline__ PairA pair_phase_a(double X, double Y, double Z, double sx, double sy, double sz,
+                                              const PhaseConst &pc, double magic)
 {
     const double ddx = sub(X, sx), ddy = sub(Y, sy), ddz = sub(Z, sz);
-    double s, root, hinv, f;
-    int q;
+    PairA a;
+    double root;
     if (MODE == AKB_PHASE_FAITHFUL) {
         // CPU0402:76-80: (dx*dx + dy*dy) + dz*dz, one rounding per operation
-        s = add(add(mul(ddx, ddx), mul(ddy, ddy)), mul(ddz, ddz));
-        sqrt_and_half_rinv(s, root, hinv);
-        const double p = mul(pc.k, root); // CPU0402:82: |phase| = fl(k*dist)
-        reduce_pio2(p, q, f);
+        const double s = add(add(mul(ddx, ddx), mul(ddy, ddy)), mul(ddz, ddz));
+        sqrt_and_half_rinv(s, root, a.h);
+        a.p = mul(pc.k, root); // CPU0402:82: |phase| = fl(k*dist)
+        a.t = fma_(a.p, pc.inv_u, magic);
     } else {
-        s = fma_(ddz, ddz, fma_(ddy, ddy, mul(ddx, ddx)));
-        sqrt_and_half_rinv(s, root, hinv);
-        // quarter turns: n = rint(r*q), f = r*q - n without ever rounding k*r
-        const double t = fma_(root, pc.q_hi, AKB_RND_MAGIC);
-        q = __double2loint(t);
-        const double n = sub(t, AKB_RND_MAGIC);
-        f = fma_(root, pc.q_hi, -n);
-        f = fma_(root, pc.q_lo, f);
-        f = mul(f, AKB_PIO2_HI);
+        const double s = fma_(ddz, ddz, fma_(ddy, ddy, mul(ddx, ddx)));
+        sqrt_and_half_rinv(s, root, a.h);
+        a.p = root;
+        a.t = fma_(root, pc.q_hi, magic); // k*r is never rounded
     }
-    double cf, sf, c, sn;
-    scaled_sincos_kernel(f, hinv, cf, sf); // (cos f, sin f) / (2r)
-    apply_quadrant(q, cf, sf, c, sn);
-    // (wr + i wi) * (c - i sn)            [exp(-i k r)/r, CPU0402:81-84]
+    return a;
+}
+
+// Byte address of table entry (q mod TBL).  The table is aligned to its own size, so the index bits
+// can be OR-ed into the base with one LOP3.  SWZ additionally XORs the 16-byte bank-group bits with
+// index bits 3..5, which spreads power-of-two index strides across the lanes of a warp.
+template <int TBL, bool SWZ>
+__device__ __forceinline__ uint32_t table_slot(int q, uint32_t table_s)
+{
+    uint32_t addr;
+    const int qs = SWZ ? (q ^ ((q >> 3) & 7)) : q;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(addr) : "r"(qs << 4), "n"((TBL - 1) << 4), "r"(table_s));
+    return addr;
+}
+
+__device__ __forceinline__ double2 lds_double2(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+// exact Cody-Waite reduction + h*(cos f, sin f): n = rint(p/u), f = p - n*u.  fma(n, -u_hi, p) is
+// exact (the difference fits in 53 bits); the u_lo term restores the bits of u beyond double.
+template <int MODE, int TBL>
+__device__ __forceinline__ void pair_phase_b(const PairA &a, const PhaseConst &pc, double t2, double &cf, double &sf)
+{
+    const double n = add(a.t, KC[KC_NEG_MAGIC]);
+    double f;
+    if (MODE == AKB_PHASE_FAITHFUL) {
+        f = fma_(n, pc.neg_u_hi, a.p);
+        f = fma_(n, pc.neg_u_lo, f);
+    } else {
+        f = fma_(a.p, pc.q_hi, -n);
+        f = fma_(a.p, pc.q_lo, f);
+        f = mul(f, pc.u);
+    }
+    const double z = mul(f, f);
+    double e1;
+    if (TBL >= 1024) {
+        e1 = fma_(z, KC[KC_T1], 1.0); // |f| <= pi/1024: the z^2/120 term is 7e-13 of |f| <= 2e-15 absolute
+    } else {
+        e1 = fma_(z, fma_(t2, z, KC[KC_T1]), 1.0); // sin f / f
+    }
+    const double c1 = fma_(z, fma_(KC[KC_TC1], z, -0.5), 1.0); // cos f
+    const double hf = mul(a.h, f);
+    sf = mul(hf, e1);
+    cf = mul(a.h, c1);
+}
+
+// rotate by the tabulated multiple (C, S) = (cos, sin)(2*pi*m/TBL) and accumulate
+// (wr + i wi) * (c - i sn)   [exp(-i k r)/r, CPU0402:81-84]
+__device__ __forceinline__ void pair_phase_c(double2 cs, double cf, double sf, double wr, double wi, double &acc_re,
+                                             double &acc_im)
+{
+    const double m1 = mul(cs.x, cf);
+    const double m2 = mul(cs.y, cf);
+    const double c = fma_(-cs.y, sf, m1);
+    const double sn = fma_(cs.x, sf, m2);
     acc_re = fma_(wr, c, acc_re);
-    acc_re = fma_(wi, sn, acc_re);
     acc_im = fma_(wi, c, acc_im);
+    acc_re = fma_(wi, sn, acc_re);
     acc_im = fma_(-wr, sn, acc_im);
 }
 
 // ---------------------------------------------------------------- pair kernel
 // grid.x: blocks of THREADS*DPT detector points; grid.y: splits of the source tiles.
 // out: [gridDim.y][M] complex partial sums (gridDim.y == 1 -> the result itself).
-template <int DPT, int MODE>
+template <int TILE, int STAGES, int TBL>
+struct PairCfg {
+    static constexpr int kTileBytes = ROWS * TILE * 8;
+    static constexpr int kTableBytes = TBL * 16;
+    // tiles | mbarriers | 2 loop constants | table (aligned to its own size: that much slack)
+    static constexpr int kSmemBytes = STAGES * kTileBytes + STAGES * 8 + 16 + 2 * kTableBytes;
+};
+
+template <int DPT, int MODE, int TILE, int STAGES, int TBL, bool SWZ>
 __global__ void __launch_bounds__(THREADS) fresnel_pairs_kernel(
     const double *__restrict__ det_x, const double *__restrict__ det_y, const double *__restrict__ det_z,
     long long M, const double *__restrict__ packed, int tiles_total, int tiles_per_split, long long n_padded,
-    PhaseConst pc, double *__restrict__ out)
+    const __grid_constant__ PhaseConst pc, double *__restrict__ out)
 {
+    using Cfg = PairCfg<TILE, STAGES, TBL>;
+    constexpr int TILE_DOUBLES = ROWS * TILE;
+    constexpr int NP = 2 * DPT; // pairs per loop iteration: DPT detector points x 2 sources
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *tiles = reinterpret_cast<double *>(smem_raw);
     const uint32_t tiles_s = smem_u32(tiles);
-    const uint32_t bars_s = smem_u32(smem_raw + STAGES * TILE_BYTES);
+    const uint32_t bars_s = tiles_s + STAGES * Cfg::kTileBytes;
+    const uint32_t consts_s = bars_s + STAGES * 8;
+    const uint32_t table_s = (consts_s + 16 + Cfg::kTableBytes - 1) & ~(uint32_t)(Cfg::kTableBytes - 1);
 
     const int t0 = blockIdx.y * tiles_per_split;
     const int t1 = min(t0 + tiles_per_split, tiles_total);
@@ -158,16 +252,30 @@ __global__ void __launch_bounds__(THREADS) fresnel_pairs_kernel(
         ai[d] = 0.0;
     }
 
+    for (int m = threadIdx.x; m < TBL; m += THREADS) {
+        double sv, cv;
+        sincospi((double)m * (2.0 / TBL), &sv, &cv); // exact argument: accurate to < 1 ulp
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(table_slot<TBL, SWZ>(m, table_s)), "d"(cv), "d"(sv) : "memory");
+    }
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(bars_s + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // Two constants share an instruction with another constant operand (fma(p, 1/u, MAGIC),
+        // fma(T2, z, T1)); a DFMA takes only one constant/uniform operand, and ptxas would re-create
+        // the second one with two IMAD.U32 per use.  Bouncing them through shared memory yields
+        // loop-invariant VECTOR registers that cannot be re-materialised.
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(consts_s), "d"(KC[KC_T2]) : "memory");
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(consts_s + 8), "d"(KC[KC_MAGIC]) : "memory");
     }
     __syncthreads();
+    double t2, magic;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t2) : "r"(consts_s) : "memory");
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(magic) : "r"(consts_s + 8) : "memory");
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES && t0 + s < t1; ++s) {
-            mbar_expect_tx(bars_s + 8 * s, TILE_BYTES);
-            tma_bulk_load(tiles_s + s * TILE_BYTES, packed + (long long)(t0 + s) * TILE_DOUBLES, TILE_BYTES,
+            mbar_expect_tx(bars_s + 8 * s, Cfg::kTileBytes);
+            tma_bulk_load(tiles_s + s * Cfg::kTileBytes, packed + (long long)(t0 + s) * TILE_DOUBLES, Cfg::kTileBytes,
                           bars_s + 8 * s);
         }
     }
@@ -186,16 +294,29 @@ __global__ void __launch_bounds__(THREADS) fresnel_pairs_kernel(
             const double2 vz = *reinterpret_cast<const double2 *>(T + 2 * TILE + j);
             const double2 vr = *reinterpret_cast<const double2 *>(T + 3 * TILE + j);
             const double2 vi = *reinterpret_cast<const double2 *>(T + 4 * TILE + j);
+            PairA a[NP];
+            double2 cs[NP];
+            double cf[NP], sf[NP];
 #pragma unroll
-            for (int d = 0; d < DPT; ++d) accumulate_pair<MODE>(X[d], Y[d], Z[d], vx.x, vy.x, vz.x, vr.x, vi.x, pc, ar[d], ai[d]);
+            for (int d = 0; d < DPT; ++d) {
+                a[2 * d] = pair_phase_a<MODE>(X[d], Y[d], Z[d], vx.x, vy.x, vz.x, pc, magic);
+                cs[2 * d] = lds_double2(table_slot<TBL, SWZ>(__double2loint(a[2 * d].t), table_s));
+                a[2 * d + 1] = pair_phase_a<MODE>(X[d], Y[d], Z[d], vx.y, vy.y, vz.y, pc, magic);
+                cs[2 * d + 1] = lds_double2(table_slot<TBL, SWZ>(__double2loint(a[2 * d + 1].t), table_s));
+            }
 #pragma unroll
-            for (int d = 0; d < DPT; ++d) accumulate_pair<MODE>(X[d], Y[d], Z[d], vx.y, vy.y, vz.y, vr.y, vi.y, pc, ar[d], ai[d]);
+            for (int i = 0; i < NP; ++i) pair_phase_b<MODE, TBL>(a[i], pc, t2, cf[i], sf[i]);
+#pragma unroll
+            for (int d = 0; d < DPT; ++d) {
+                pair_phase_c(cs[2 * d], cf[2 * d], sf[2 * d], vr.x, vi.x, ar[d], ai[d]);
+                pair_phase_c(cs[2 * d + 1], cf[2 * d + 1], sf[2 * d + 1], vr.y, vi.y, ar[d], ai[d]);
+            }
         }
         __syncthreads(); // every thread is done with this stage
         if (threadIdx.x == 0 && t + STAGES < t1) {
-            mbar_expect_tx(bars_s + 8 * stage, TILE_BYTES);
-            tma_bulk_load(tiles_s + stage * TILE_BYTES, packed + (long long)(t + STAGES) * TILE_DOUBLES, TILE_BYTES,
-                          bars_s + 8 * stage);
+            mbar_expect_tx(bars_s + 8 * stage, Cfg::kTileBytes);
+            tma_bulk_load(tiles_s + stage * Cfg::kTileBytes, packed + (long long)(t + STAGES) * TILE_DOUBLES,
+                          Cfg::kTileBytes, bars_s + 8 * stage);
         }
         if (++stage == STAGES) {
             stage = 0;
@@ -232,41 +353,80 @@ __global__ void fill_zero_kernel(double *p, long long n)
     if (i < n) p[i] = 0.0;
 }
 
-// k*(2/pi) as an unevaluated sum hi+lo (double-double product, ~2^-100 relative)
-void quarter_turns_per_metre(double k, double &hi, double &lo)
+// ---------------------------------------------------------------- host side
+// a * (b_hi + b_lo) as an unevaluated sum hi + lo (~2^-100 relative)
+void dd_scale(double a, double b_hi, double b_lo, double &hi, double &lo)
 {
-    const double t_hi = 6.36619772367581382433e-01;  // 2/pi
-    const double t_lo = -3.935735335036497e-17;      // 2/pi - t_hi
-    double ph = k * t_hi;
-    double pl = __builtin_fma(k, t_hi, -ph) + k * t_lo;
+    double ph = a * b_hi;
+    double pl = __builtin_fma(a, b_hi, -ph) + a * b_lo;
     hi = ph + pl;
     lo = pl - (hi - ph);
 }
 
-template <int DPT, int MODE>
-int launch_pairs(const double *dx, const double *dy, const double *dz, long long M, const double *packed,
-                 int tiles_total, long long n_padded, PhaseConst pc, double *out, int splits, int tiles_per_split,
-                 cudaStream_t st)
+PhaseConst make_phase_const(double k, int table)
 {
-    auto kern = fresnel_pairs_kernel<DPT, MODE>;
-    AKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    dim3 grid((unsigned)((M + THREADS * DPT - 1) / (THREADS * DPT)), (unsigned)splits);
-    kern<<<grid, THREADS, SMEM_BYTES, st>>>(dx, dy, dz, M, packed, tiles_total, tiles_per_split, n_padded, pc, out);
-    AKB_LAUNCH_CHECK();
-    return AKB_OK;
+    const double pi_hi = 3.141592653589793116e+00, pi_lo = 1.2246467991473532e-16;
+    const double ipi_hi = 3.183098861837906912e-01, ipi_lo = -1.9678676675182486e-17; // 1/pi
+    // u = 2*pi/table: a power-of-two multiple of pi, exact in both words
+    const double su = 2.0 / table, si = table / 2.0;
+    PhaseConst pc;
+    pc.k = k;
+    pc.u = pi_hi * su;
+    pc.inv_u = ipi_hi * si;
+    pc.neg_u_hi = -pi_hi * su;
+    pc.neg_u_lo = -pi_lo * su;
+    dd_scale(k, ipi_hi * si, ipi_lo * si, pc.q_hi, pc.q_lo);
+    return pc;
 }
 
-template <int DPT, int MODE>
-int resident_blocks_per_sm(int *out)
+struct KernelEntry {
+    const char *name;
+    int dpt, tile, stages, table;
+    const void *fn[2]; // per mode
+    int smem;
+};
+
+template <int DPT, int TILE, int STAGES, int TBL, bool SWZ>
+KernelEntry make_entry(const char *name)
 {
-    auto kern = fresnel_pairs_kernel<DPT, MODE>;
-    AKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    AKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kern, THREADS, SMEM_BYTES));
-    if (*out < 1) *out = 1;
-    return AKB_OK;
+    KernelEntry e;
+    e.name = name;
+    e.dpt = DPT;
+    e.tile = TILE;
+    e.stages = STAGES;
+    e.table = TBL;
+    e.fn[0] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_FAITHFUL, TILE, STAGES, TBL, SWZ>);
+    e.fn[1] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_EXACT, TILE, STAGES, TBL, SWZ>);
+    e.smem = PairCfg<TILE, STAGES, TBL>::kSmemBytes;
+    return e;
 }
 
-constexpr int DPT_MAIN = 2;
+// Tuning variants; index 0 is the default.  AKB_FRESNEL_VARIANT=<n> selects another one.
+const KernelEntry *kernel_table(int *count)
+{
+    static const KernelEntry entries[] = {
+        make_entry<4, 512, 2, 1024, false>("dpt4 tile512x2 table1024"),
+        make_entry<2, 512, 2, 1024, false>("dpt2 tile512x2 table1024"),
+        make_entry<4, 512, 2, 512, false>("dpt4 tile512x2 table512"),
+        make_entry<1, 512, 2, 1024, false>("dpt1 tile512x2 table1024"),
+        make_entry<4, 512, 2, 1024, true>("dpt4 tile512x2 table1024 swizzled"),
+    };
+    *count = (int)(sizeof(entries) / sizeof(entries[0]));
+    return entries;
+}
+
+const KernelEntry &selected_kernel()
+{
+    int n = 0;
+    const KernelEntry *e = kernel_table(&n);
+    static int idx = -1;
+    if (idx < 0) {
+        const char *v = getenv("AKB_FRESNEL_VARIANT");
+        int want = v ? atoi(v) : 0;
+        idx = (want >= 0 && want < n) ? want : 0;
+    }
+    return e[idx];
+}
 
 // optional in-library timing of the last akb_fresnel_sum call of this thread (bench.py roofline)
 struct Timing {
@@ -304,12 +464,15 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
         return AKB_OK;
     }
     AKB_REQUIRE(src_x && src_y && src_z && src_u, "source pointers must not be NULL");
-    AKB_REQUIRE(k >= 0.0 && k < 3.0e13, "wave number k must be in [0, 3e13)");
+    AKB_REQUIRE(k >= 0.0 && k < 1.0e12, "wave number k must be in [0, 1e12) (k*r must stay below 2^48 units)");
 
     int device = 0;
     AKB_CUDA(cudaGetDevice(&device));
     tune_pool(device);
     const int sms = sm_count(device);
+    const KernelEntry &ke = selected_kernel();
+    const void *kern = ke.fn[mode];
+    const int TILE = ke.tile;
 
     const int tiles_total = (int)((N + TILE - 1) / TILE);
     const long long padded = (long long)tiles_total * TILE;
@@ -317,11 +480,11 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
 
     // ---- plan: split the source tiles so the grid fills whole waves
     int per_sm = 1;
-    int rc = (mode == AKB_PHASE_FAITHFUL) ? resident_blocks_per_sm<DPT_MAIN, AKB_PHASE_FAITHFUL>(&per_sm)
-                                          : resident_blocks_per_sm<DPT_MAIN, AKB_PHASE_EXACT>(&per_sm);
-    if (rc) return rc;
+    AKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ke.smem));
+    AKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, ke.smem));
+    if (per_sm < 1) per_sm = 1;
     const long long slots = (long long)sms * per_sm;
-    const long long blocks_x = (M + THREADS * DPT_MAIN - 1) / (THREADS * DPT_MAIN);
+    const long long blocks_x = (M + THREADS * ke.dpt - 1) / (THREADS * ke.dpt);
     int splits = 1;
     {
         double best = -1.0;
@@ -342,8 +505,9 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
             if (eff >= 0.97) break;
         }
     }
-    const int tiles_per_split = (tiles_total + splits - 1) / splits;
+    int tiles_per_split = (tiles_total + splits - 1) / splits;
 
+    int rc;
     g_timing.valid = false;
     g_timing.splits = splits;
     g_timing.per_sm = per_sm;
@@ -355,20 +519,22 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     if (splits > 1) AKB_CUDA(cudaMallocAsync(&partial, (size_t)splits * M * 2 * sizeof(double), st));
 
     pack_sources_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, st>>>(src_x, src_y, src_z, src_u, src_ds, N,
-                                                                          padded, packed);
+                                                                          padded, TILE, packed);
     AKB_LAUNCH_CHECK();
 
-    PhaseConst pc;
-    pc.k = k;
-    quarter_turns_per_metre(k, pc.q_hi, pc.q_lo);
+    PhaseConst pc = make_phase_const(k, ke.table);
     double *dst = splits > 1 ? partial : out;
     if ((rc = timing_mark(1, st))) return rc;
-    rc = (mode == AKB_PHASE_FAITHFUL)
-             ? launch_pairs<DPT_MAIN, AKB_PHASE_FAITHFUL>(det_x, det_y, det_z, M, packed, tiles_total, n_padded, pc,
-                                                           dst, splits, tiles_per_split, st)
-             : launch_pairs<DPT_MAIN, AKB_PHASE_EXACT>(det_x, det_y, det_z, M, packed, tiles_total, n_padded, pc, dst,
-                                                        splits, tiles_per_split, st);
-    if (rc) return rc;
+    {
+        long long M_ = M;
+        int tt = tiles_total;
+        const double *pk = packed;
+        void *args[] = {(void *)&det_x, (void *)&det_y, (void *)&det_z, (void *)&M_, (void *)&pk, (void *)&tt,
+                        (void *)&tiles_per_split, (void *)&n_padded, (void *)&pc, (void *)&dst};
+        dim3 grid((unsigned)blocks_x, (unsigned)splits);
+        AKB_CUDA(cudaLaunchKernel(kern, grid, dim3(THREADS), args, (size_t)ke.smem, st));
+        count_launch();
+    }
     if ((rc = timing_mark(2, st))) return rc;
     if (splits > 1) {
         reduce_partials_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(
@@ -405,6 +571,8 @@ extern "C" int akb_fresnel_last_timing(double *pairs_ms, double *total_ms, int *
     return AKB_OK;
 }
 
+extern "C" const char *akb_fresnel_variant_name(void) { return selected_kernel().name; }
+
 extern "C" int akb_fresnel_sum_host(const double *det_x, const double *det_y, const double *det_z, int64_t M,
                                     const double *src_x, const double *src_y, const double *src_z,
                                     const double *src_u, const double *src_ds, int64_t N, double k, double *out,
@@ -420,7 +588,8 @@ extern "C" int akb_fresnel_sum_host(const double *det_x, const double *det_y, co
     AKB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     const size_t mb = (size_t)M * sizeof(double), nb = (size_t)(N > 0 ? N : 1) * sizeof(double);
     double *d = nullptr;
-    // one slab: det xyz (3M) | out (2M) | src xyz (3N) | u (2N) | ds (N)
+    // one slab: out (2M) | u (2N) | det xyz (3M) | src xyz (3N) | ds (N); the two complex arrays
+    // come first so that they stay 16-byte aligned for any M, N
     const size_t total = 5 * mb + 6 * nb;
     int rc = AKB_OK;
     cudaError_t e = cudaMallocAsync(&d, total, st);
@@ -429,9 +598,10 @@ extern "C" int akb_fresnel_sum_host(const double *det_x, const double *det_y, co
         cudaStreamDestroy(st);
         return AKB_ERR_CUDA;
     }
-    double *ddx = d, *ddy = d + M, *ddz = d + 2 * M, *dout = d + 3 * M;
-    double *dsx = d + 5 * M, *dsy = dsx + (N > 0 ? N : 1), *dsz = dsy + (N > 0 ? N : 1), *du = dsz + (N > 0 ? N : 1);
-    double *dds = du + 2 * (N > 0 ? N : 1);
+    const int64_t Nn = N > 0 ? N : 1;
+    double *dout = d, *du = d + 2 * M;
+    double *ddx = du + 2 * Nn, *ddy = ddx + M, *ddz = ddy + M;
+    double *dsx = ddz + M, *dsy = dsx + Nn, *dsz = dsy + Nn, *dds = dsz + Nn;
 #define H2D(dst, src, bytes)                                                                    \
     if (rc == AKB_OK && (bytes) > 0 && cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { \
         set_error("H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));              \

@@ -36,7 +36,8 @@ extern "C" {
 
 /* phase arithmetic of akb_fresnel_sum */
 #define AKB_PHASE_FAITHFUL 0 /* r and k*r rounded exactly like NumPy/numba (default) */
-#define AKB_PHASE_EXACT 1    /* fused r^2, k*r never rounded: phase reduced in quarter turns */
+#define AKB_PHASE_EXACT 1    /* fused r^2; the product k*r is never rounded (reduced in quarter \
+                                turns); r itself is still one rounded double */
 
 /* entries of the int[AKB_NFLAGS] status block written by the ray kernels */
 #define AKB_FLAG_MISS 0      /* number of rays with not(D > 0)                  ER3D:31 */
@@ -91,6 +92,9 @@ int akb_shard_range(int64_t total, int nranks, int rank, int64_t *begin, int64_t
 int akb_fresnel_timing(int enable);
 int akb_fresnel_last_timing(double *pairs_ms, double *total_ms, int *splits, int64_t *blocks_x,
                             int *blocks_per_sm);
+
+/* name of the pair-kernel variant in use (default, or chosen with AKB_FRESNEL_VARIANT=<n>) */
+const char *akb_fresnel_variant_name(void);
 
 /* kernel launches issued by the calling thread since the last reset (bench.py "gpu_launches") */
 int64_t akb_launch_count(int reset);

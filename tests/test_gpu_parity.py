@@ -112,7 +112,9 @@ def test_fresnel_exact_mode(akb, golden):
     faithful = akb.fresnel_sum(c["x"], c["y"], c["z"], c["sx"], c["sy"], c["sz"], c["u"], float(c["k"]), c["ds"])
     e_exact, e_faithful = rel_l2(exact, truth), rel_l2(faithful, truth)
     print(f"146 m stage vs 80-bit: exact {e_exact:.2e}, faithful(=reference) {e_faithful:.2e}")
-    assert e_exact < 5e-7 and e_exact < e_faithful
+    # r itself is still a rounded double (ulp(146 m)/2 * k = 6.6e-5 rad at 1.35 nm), so EXACT only
+    # removes the second rounding, fl(k*r): a little closer to the truth than the reference is.
+    assert e_exact < e_faithful and e_exact < 1e-4
 
 
 # ------------------------------------------------------------------ path A vs the oracle

@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Estimate FP64-pipe cycles of a kernel's hot loop on sm_100a from its SASS, with the measured rule
+  cycles(FP64 instr) = max(2, #distinct 64-bit vector-register operands not served by .reuse)
+(tools/ubench/fp64_operands.cu, fp64_reuse.cu).  Usage: sass_cost.py <lib.so> <kernel-substring> [pairs-per-iteration]"""
+import re
+import subprocess
+import sys
+
+lib, pat = sys.argv[1], sys.argv[2]
+pairs = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+for b in re.split(r"\n\s*Function : ", txt):
+    name = b.split("\n", 1)[0]
+    if pat not in name:
+        continue
+    ins = []
+    for line in b.split("\n"):
+        m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);", line)
+        if m:
+            ins.append((int(m.group(1), 16), m.group(2).strip()))
+    best = None
+    for addr, text in ins:
+        m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d,\s*)?0x([0-9a-f]+)", text)
+        if m and int(m.group(1), 16) < addr:
+            tgt = int(m.group(1), 16)
+            body = [t for a, t in ins if tgt <= a <= addr]
+            nd = sum(1 for t in body if re.match(r"D(FMA|MUL|ADD)", t))
+            if best is None or nd > best[0]:
+                best = (nd, body)
+    nd, body = best
+    cyc = 0
+    three = 0
+    prev_reuse = {}  # slot -> register kept by the previous FP64 instruction of this warp
+    other = 0
+    for t in body:
+        m = re.match(r"(DFMA|DMUL|DADD)\s+(R\d+),\s*(.*)", t)
+        if not m:
+            other += 1
+            continue
+        ops = [o.strip() for o in m.group(3).split(",")]
+        regs = []
+        keep = {}
+        for slot, o in enumerate(ops):
+            r = re.match(r"[-|]*\|?(R\d+)(\.reuse)?", o)
+            if r and not o.lstrip("-|").startswith("RZ"):
+                reg = r.group(1)
+                if prev_reuse.get(slot) != reg:
+                    regs.append(reg)
+                if r.group(2):
+                    keep[slot] = reg
+        prev_reuse = keep
+        d = len(set(regs))
+        three += d >= 3
+        cyc += max(2, d)
+    print(f"{name[:100]}\n  FP64 instrs {nd}, 3-read instrs {three}, FP64 pipe cycles {cyc} ({cyc / pairs:.1f}/pair), "
+          f"other instrs {other} ({other / pairs:.1f}/pair)")
