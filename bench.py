@@ -38,7 +38,8 @@ GRID = 512            # focal grid side per rank
 RAYS = 1000           # ray grid side -> 1e6 source points
 WAVELENGTH = 13.5e-9  # CPU0402:243
 ALG_FLOP_PER_TERM = 23.0   # SURVEY.md 8(d) convention
-EXEC_FLOP_PER_TERM = 66.0  # 25 DFMA (x2) + 16 DMUL/DADD actually issued per pair (faithful mode, from SASS)
+EXEC_FLOP_PER_TERM = 52.0  # 17 DFMA (x2) + 12 DMUL + 6 DADD issued per pair (faithful mode, counted in the SASS loop)
+FP64_INSTR_PER_TERM = 35.0  # each occupies the FP64 pipe of an SM sub-partition for >= 2 cycles
 
 
 def measured_peaks():
@@ -314,7 +315,7 @@ def run_ours(args):
         pair_terms = float(RAYS * RAYS) * count
         achieved = pair_terms * ALG_FLOP_PER_TERM / (pair_mean * 1e-3) / 1e12
         roofline = {
-            "kernel": "fresnel_pairs_kernel<2, faithful>", "bound": "fp64",
+            "kernel": "fresnel_pairs_kernel<faithful> [%s]" % L.akb_fresnel_variant_name().decode(), "bound": "fp64",
             "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
             "traffic": None,
             "peak_source": "on-box DFMA microbenchmark (akb_fp64_peak_probe, measured in this run); "
@@ -323,6 +324,10 @@ def run_ours(args):
             "executed_flop_per_term": EXEC_FLOP_PER_TERM,
             "achieved_exec": achieved * EXEC_FLOP_PER_TERM / ALG_FLOP_PER_TERM,
             "frac_exec": achieved * EXEC_FLOP_PER_TERM / ALG_FLOP_PER_TERM / fp64_peak,
+            # issue-slot view of the same pipe: a DFMA-only stream reaches `peak` with one FP64
+            # instruction per 2 cycles; this kernel issues FP64_INSTR_PER_TERM of them per term
+            "fp64_instr_per_term": FP64_INSTR_PER_TERM,
+            "frac_pipe_issue": (pair_terms / (pair_mean * 1e-3)) * FP64_INSTR_PER_TERM * 2.0 / (fp64_peak * 1e12),
             "kernel_ms": pair_mean, "kernel_share_of_step": pair_mean * args.steps / total_ms,
             "terms_per_s_kernel": pair_terms / (pair_mean * 1e-3), "plan": plan,
         }
