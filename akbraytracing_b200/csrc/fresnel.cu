@@ -433,6 +433,7 @@ struct Timing {
     bool enabled = false;
     bool valid = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // call start, pairs start, pairs end, call end
+    int device = -1;                                          // events belong to one device
     int splits = 0, per_sm = 0;
     long long blocks_x = 0;
 };
@@ -441,6 +442,15 @@ thread_local Timing g_timing;
 int timing_mark(int idx, cudaStream_t st)
 {
     if (!g_timing.enabled) return AKB_OK;
+    int device = 0;
+    AKB_CUDA(cudaGetDevice(&device));
+    if (device != g_timing.device) {
+        for (auto &e : g_timing.ev) {
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
+        g_timing.device = device;
+    }
     if (!g_timing.ev[idx]) AKB_CUDA(cudaEventCreate(&g_timing.ev[idx]));
     AKB_CUDA(cudaEventRecord(g_timing.ev[idx], st));
     return AKB_OK;
@@ -582,7 +592,8 @@ extern "C" int akb_fresnel_sum_host(const double *det_x, const double *det_y, co
     if (M == 0) return AKB_OK;
     AKB_REQUIRE(det_x && det_y && det_z && out, "detector/out pointers must not be NULL");
     AKB_REQUIRE(N == 0 || (src_x && src_y && src_z && src_u), "source pointers must not be NULL");
-    AKB_CUDA(cudaSetDevice(device));
+    if (device >= 0) AKB_CUDA(cudaSetDevice(device)); // device < 0: the calling thread's current device
+    AKB_CUDA(cudaGetDevice(&device));
     tune_pool(device);
     cudaStream_t st;
     AKB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));

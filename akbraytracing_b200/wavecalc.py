@@ -29,7 +29,7 @@ def _any_torch(*arrays) -> bool:
     return any(_lib.is_torch(a) for a in arrays)
 
 
-def _fresnel_host(x, y, z, sx, sy, sz, u, k, ds, mode, device=0) -> np.ndarray:
+def _fresnel_host(x, y, z, sx, sy, sz, u, k, ds, mode, device=-1) -> np.ndarray:
     x, y, z = _lib.as_f64(x), _lib.as_f64(y), _lib.as_f64(z)
     sx, sy, sz = _lib.as_f64(sx), _lib.as_f64(sy), _lib.as_f64(sz)
     u = _lib.as_c128(u)
@@ -89,7 +89,7 @@ def fresnel_sum(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds=None, mod
     """u_i = sum_j (u_j ds_j) exp(-1j k r_ij)/r_ij on one B200 (CPU0402:71-85 + :102)."""
     if _any_torch(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, ds):
         return _fresnel_device(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, mode, device)
-    return _fresnel_host(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, mode, 0 if device is None else device)
+    return _fresnel_host(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, mode, -1 if device is None else device)
 
 
 def forward_propagation_numpy_batch(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, num_cores=None):

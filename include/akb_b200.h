@@ -11,8 +11,8 @@
  * Conventions
  *   - every function returns 0 on success, <0 on error; akb_last_error() (thread local)
  *     describes the last failure of the calling thread;
- *   - "_host" entry points take HOST pointers, do H2D + kernels + D2H on `device`, are
- *     synchronous, and apply the reference's all-or-nothing NaN / normalisation semantics;
+ *   - "_host" entry points take HOST pointers, do H2D + kernels + D2H on `device` (< 0: the
+ *     calling thread's current device), are synchronous, and apply the reference's all-or-nothing NaN / normalisation semantics;
  *   - all other entry points take DEVICE pointers, are asynchronous on `stream`
  *     (a cudaStream_t passed as void*, NULL = legacy default stream) and never synchronise;
  *   - arrays are the reference's: float64 C-contiguous (3,N) (row 0 = x, row 1 = y,
