@@ -381,3 +381,54 @@ def test_single_process_multi_device(akb, torch, golden):
     got = akb.forward_propagation_cupy_batch_multi_gpu(c["x"], c["y"], c["z"], c["sx"], c["sy"], c["sz"], c["u"],
                                                        float(c["k"]), c["ds"])
     assert rel_l2(got, c["ref"]) <= 1e-12
+
+
+# ------------------------------------------------------------------ next rows: PSF, stage chain
+
+@pytest.mark.parametrize("tag,kw", [("plain", dict(pad_factor=2)),
+                                    ("hann", dict(pad_factor=3, window="hann", pupil_dy_m=1.5e-4))])
+def test_psf_on_device_vs_reference_golden(akb, torch, golden, tag, kw):
+    g = golden("psf_ref")
+    I, x, y, E = akb.compute_psf_fft(g["opd"], g["amp"], 13.5e-9, 1e-4, 0.3, return_efield=True, **kw)
+    assert np.allclose(I, g[f"{tag}/I"], rtol=1e-10, atol=1e-16)
+    assert np.array_equal(x, g[f"{tag}/x"]) and np.allclose(E, g[f"{tag}/E"], rtol=1e-9, atol=1e-15)
+    It, _, _ = akb.compute_psf_fft(torch.as_tensor(g["opd"]).cuda(), torch.as_tensor(g["amp"]).cuda(), 13.5e-9, 1e-4, 0.3, **kw)
+    assert It.is_cuda and np.allclose(It.cpu().numpy(), g[f"{tag}/I"], rtol=1e-10, atol=1e-16)
+
+
+@pytest.mark.parametrize("tag,K", [("c3", 2), ("c4", 4)])
+def test_stage_chain_files_and_fields(akb, torch, tmp_path, tag, K):
+    """trace -> write_handoff (reference file formats) -> run_stage_chain with device-resident fields,
+    checked stage by stage against the oracle (the chain of CPU0402:247-375)."""
+    from akbraytracing_b200 import workloads
+    n, G = 24, 12
+    coeffs, neg, plane, ray, src = workloads.chain_inputs(tag, n, "cuda")
+    tr = akb.trace_chain(coeffs, neg, plane, ray, src)
+    folder = tmp_path / "handoff"
+    akb.write_handoff(str(folder), src[:, 0], [tr["points"][k] for k in range(K)], (n, n), tr["det"],
+                      det_defocus=tr["det"], option_HighNA=True, focus_shape=(G, G), defocus=1e-3)
+    h = akb.load_handoff(str(folder))
+    assert h["conditions"]["option_AKB"] == (K == 4) and len(h["mirrors"]) == K
+    assert h["mirrors"][0].shape == (4, n * n) and h["gridImage"].shape == (3, G * G)
+    dS_ref = oracle.calc_dS(h["mirrors"][0][:3], n, n)
+    assert np.allclose(h["mirrors"][0][3].reshape(n, n), dS_ref, rtol=1e-12, atol=0)
+    out = akb.run_stage_chain(str(folder), out_dir=str(tmp_path / "out"))
+    # oracle chain
+    k = 2 * np.pi / 13.5e-9
+    u = np.ones(1, complex); bx, by, bz = (np.array([v]) for v in h["source"]); ds = np.ones(1)
+    for i, pts in enumerate(h["mirrors"]):
+        u = oracle.fresnel_sum(pts[0], pts[1], pts[2], bx, by, bz, u, k, ds)
+        err = rel_l2(out[f"M{i + 1}"], u)
+        assert err <= 1e-11, (i, err)
+        bx, by, bz, ds = pts[0], pts[1], pts[2], pts[3]
+    grid = h["gridImage"]
+    mean = grid.mean(axis=1, keepdims=True)
+    grid = (grid - mean) * 2.0 + mean
+    ref = oracle.fresnel_sum(grid[0], grid[1], grid[2], bx, by, bz, u, k, ds)
+    assert rel_l2(out["Image"], ref) <= 1e-10
+    assert int(np.argmax(np.abs(out["Image"]))) == int(np.argmax(np.abs(ref)))
+    with np.load(tmp_path / "out" / "complex_data_Image.npz") as z:
+        assert np.array_equal(z["data"], out["Image"])
+    # resume: a stored M1 is loaded instead of recomputed (CPU0402:261-265)
+    again = akb.run_stage_chain(str(folder), resume_dir=str(tmp_path / "out"))
+    assert np.array_equal(again["M1"], out["M1"]) and rel_l2(again["Image"], out["Image"]) <= 1e-13

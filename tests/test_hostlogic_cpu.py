@@ -1,0 +1,47 @@
+"""CPU-only tests of host logic that sits beside the hot path: hand-off file parsing, the PSF
+restatement on torch (run on the CPU device here, on cuda in test_gpu_parity.py)."""
+import numpy as np
+import pytest
+
+
+def test_parse_conditions_follows_reference_substring_rules():
+    from akbraytracing_b200.stagechain import parse_conditions
+    text = ("Conditions\n====================\ntime: 20250404_101112\n"
+            "grid pitch_y: 3.9e-09\ngrid size_y: 2e-06\n"
+            "grid pix_y: 64\ngrid pix_z: 48\ngrid pix_H1: 101\ngrid pix_V1: 99\ngrid pix_H2: 51\ngrid pix_V2: 49\n"
+            "option_AKB: True\noption_HighNA: False\ndefocusForWave: 0.001\n")
+    c = parse_conditions(text)
+    assert (c["pix_y"], c["pix_z"]) == (64, 48)
+    assert (c["ray_num_H1"], c["ray_num_V1"], c["ray_num_H2"], c["ray_num_V2"]) == (101, 99, 51, 49)  # CPU0402:224-231
+    assert c["option_AKB"] is True and c["option_HighNA"] is False
+    # older files only carry pix_y / pix_z: they seed the ray counts too (CPU0402:210-217)
+    c = parse_conditions("grid pix_y: 33\ngrid pix_z: 31\noption_AKB: False\noption_HighNA: True\n")
+    assert (c["ray_num_H1"], c["ray_num_H2"], c["ray_num_V1"], c["ray_num_V2"]) == (33, 33, 31, 31)
+    # 'grid pix_H:' / 'grid pix_V:' cross-assign (CPU0402:218-223)
+    c = parse_conditions("grid pix_H: 7\ngrid pix_V: 9\n")
+    assert (c["ray_num_H1"], c["ray_num_V2"], c["ray_num_V1"], c["ray_num_H2"]) == (7, 7, 9, 9)
+
+
+def test_focal_grids_layout():
+    from akbraytracing_b200.stagechain import focal_grids
+    det = np.array([[1.0, 1.2, 1.1], [-2e-6, 4e-6, 0.0], [5e-6, 7e-6, 6e-6]])
+    grid, yg, zg = focal_grids(det, 5, 3)
+    assert grid.shape == (3, 15) and np.allclose(grid[0], 1.1)
+    assert np.allclose(yg, np.linspace(1e-6 - 1e-6, 1e-6 + 1e-6, 5)) and np.allclose(zg, np.linspace(5e-6, 7e-6, 3))
+    assert np.array_equal(grid[1, :5], yg) and np.array_equal(grid[2, ::5], zg)  # np.meshgrid(y, z) order: y fastest
+
+
+@pytest.mark.parametrize("tag,kw", [("plain", dict(pad_factor=2)),
+                                    ("hann", dict(pad_factor=3, window="hann", pupil_dy_m=1.5e-4))])
+def test_psf_matches_reference_golden_on_cpu_device(golden, tag, kw):
+    from akbraytracing_b200.psf import compute_psf_fft, psf_to_db
+    g = golden("psf_ref")
+    I, x, y, E = compute_psf_fft(g["opd"], g["amp"], 13.5e-9, 1e-4, 0.3, return_efield=True, device="cpu", **kw)
+    assert np.allclose(I, g[f"{tag}/I"], rtol=1e-10, atol=1e-16)
+    assert np.array_equal(x, g[f"{tag}/x"]) and np.array_equal(y, g[f"{tag}/y"])
+    assert np.allclose(E, g[f"{tag}/E"], rtol=1e-9, atol=1e-15)
+    assert psf_to_db(I).min() >= -60.0 - 1e-9
+    with pytest.raises(ValueError):
+        compute_psf_fft(g["opd"], g["amp"][:-1], 13.5e-9, 1e-4, 0.3, device="cpu")
+    with pytest.raises(ValueError):
+        compute_psf_fft(g["opd"], g["amp"], 13.5e-9, 1e-4, 0.3, window="hamming", device="cpu")
