@@ -306,11 +306,33 @@ __global__ void __launch_bounds__(THREADS) fresnel_pairs_kernel(
             }
 #pragma unroll
             for (int i = 0; i < NP; ++i) pair_phase_b<MODE, TBL>(a[i], pc, t2, cf[i], sf[i]);
+            // phase C: rotate by the table entry, then accumulate.  The accumulation is ordered by
+            // source and by operation so that consecutive DFMAs share their first operand (w_re or
+            // w_im of one source): served by the operand-reuse cache, they read 2 registers, not 3.
+            double c[NP], sn[NP];
 #pragma unroll
-            for (int d = 0; d < DPT; ++d) {
-                pair_phase_c(cs[2 * d], cf[2 * d], sf[2 * d], vr.x, vi.x, ar[d], ai[d]);
-                pair_phase_c(cs[2 * d + 1], cf[2 * d + 1], sf[2 * d + 1], vr.y, vi.y, ar[d], ai[d]);
+            for (int i = 0; i < NP; ++i) {
+                const double m1 = mul(cs[i].x, cf[i]);
+                const double m2 = mul(cs[i].y, cf[i]);
+                c[i] = fma_(-cs[i].y, sf[i], m1);
+                sn[i] = fma_(cs[i].x, sf[i], m2);
             }
+#pragma unroll
+            for (int d = 0; d < DPT; ++d) ar[d] = fma_(vr.x, c[2 * d], ar[d]);
+#pragma unroll
+            for (int d = 0; d < DPT; ++d) ai[d] = fma_(-vr.x, sn[2 * d], ai[d]);
+#pragma unroll
+            for (int d = 0; d < DPT; ++d) ai[d] = fma_(vi.x, c[2 * d], ai[d]);
+#pragma unroll
+            for (int d = 0; d < DPT; ++d) ar[d] = fma_(vi.x, sn[2 * d], ar[d]);
+#pragma unroll
+            for (int d = 0; d < DPT; ++d) ar[d] = fma_(vr.y, c[2 * d + 1], ar[d]);
+#pragma unroll
+            for (int d = 0; d < DPT; ++d) ai[d] = fma_(-vr.y, sn[2 * d + 1], ai[d]);
+#pragma unroll
+            for (int d = 0; d < DPT; ++d) ai[d] = fma_(vi.y, c[2 * d + 1], ai[d]);
+#pragma unroll
+            for (int d = 0; d < DPT; ++d) ar[d] = fma_(vi.y, sn[2 * d + 1], ar[d]);
         }
         __syncthreads(); // every thread is done with this stage
         if (threadIdx.x == 0 && t + STAGES < t1) {
