@@ -432,3 +432,72 @@ def test_stage_chain_files_and_fields(akb, torch, tmp_path, tag, K):
     # resume: a stored M1 is loaded instead of recomputed (CPU0402:261-265)
     again = akb.run_stage_chain(str(folder), resume_dir=str(tmp_path / "out"))
     assert np.array_equal(again["M1"], out["M1"]) and rel_l2(again["Image"], out["Image"]) <= 1e-13
+
+
+# ------------------------------------------------------------------ production sizes, threads, host ABI
+
+def test_production_sized_surfaces(akb):
+    """4097 x 4097 = 1.7e7 points per surface (the reference's dataset names, GPU0402:262-263):
+    (a) the source -> M1 stage: 1 source, 1.7e7 detector points, checked in full;
+    (b) a 1.7e7-point source surface against 768 detector points, 48 of them checked."""
+    n = 4097 * 4097
+    rng = np.random.default_rng(17)
+    k = 2 * np.pi / 1.35e-9
+    x = 146.0 + rng.uniform(-0.05, 0.05, n); y = rng.uniform(-5e-3, 5e-3, n); z = rng.uniform(-5e-3, 5e-3, n)
+    one = np.zeros(1)
+    got = akb.fresnel_sum(x, y, z, one, one, one, np.ones(1, complex), k, np.ones(1))
+    ref = oracle.fresnel_sum(x, y, z, one, one, one, np.ones(1, complex), k, np.ones(1))
+    assert rel_l2(got, ref) <= 1e-12   # k r ~ 7e11 rad: reproduces the reference's double rounding exactly
+    u = np.exp(2j * np.pi * rng.uniform(size=n)); ds = rng.uniform(1e-12, 2e-12, n)
+    m = 768
+    dx = 146.2 + rng.uniform(-1e-3, 1e-3, m); dy = rng.uniform(-1e-3, 1e-3, m); dz = rng.uniform(-1e-3, 1e-3, m)
+    got = akb.fresnel_sum(dx, dy, dz, x, y, z, u, k, ds)
+    sel = np.arange(0, m, 16)
+    ref = oracle.fresnel_sum(dx[sel], dy[sel], dz[sel], x, y, z, u, k, ds)
+    err = rel_l2(got[sel], ref)
+    print(f"1.7e7-point source surface: rel-L2 vs oracle = {err:.3e}")
+    assert err <= 1e-11
+
+
+def test_concurrent_host_threads(akb, torch, golden):
+    """GPU0402_multi.py drives the devices from one host thread each (MULTI:213-225): the entry points
+    must be re-entrant.  Four threads, each with its own stream, same device."""
+    import threading
+    c = golden("fresnel_ref").group("mirror_to_mirror")
+    t = {k: torch.as_tensor(np.ascontiguousarray(v)).cuda() for k, v in c.items() if k not in ("k", "ref", "ref_numpy")}
+    results, errors = [None] * 4, []
+
+    def work(i):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for _ in range(5):
+                    out = akb.fresnel_sum(t["x"], t["y"], t["z"], t["sx"], t["sy"], t["sz"], t["u"], float(c["k"]), t["ds"])
+                torch.cuda.current_stream().synchronize()
+                results[i] = out.cpu().numpy()
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+    torch.cuda.synchronize()
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [th.start() for th in threads]
+    [th.join() for th in threads]
+    assert not errors
+    for r in results:
+        assert rel_l2(r, c["ref"]) <= 1e-12 and np.array_equal(r, results[0])
+
+
+def test_intersect_reflect_host_abi(akb, golden):
+    """akb_intersect_reflect_host with plain host pointers: values, miss -> all NaN, flags."""
+    g = golden("ray_er3d_ref")
+    hp = akb._lib.host_ptr
+    L = akb._lib.load()
+    co = np.ascontiguousarray(g["general/coeffs"]); ray = np.ascontiguousarray(g["single/ray"])
+    src = np.ascontiguousarray(g["general/source"])
+    N = ray.shape[1]
+    p, n, r = np.empty((3, N)), np.empty((3, N)), np.empty((3, N))
+    flags = np.zeros(4, np.int32)
+    akb._lib.check(L.akb_intersect_reflect_host(hp(co), hp(ray), hp(src), N, 0, hp(p), hp(n), hp(r), hp(flags), -1), "host")
+    assert flags[0] == 0
+    assert np.array_equal(p, g["general/points"]) and np.array_equal(n, g["general/normal"]) and np.array_equal(r, g["general/reflect"])
+    co1 = np.ascontiguousarray(g["single/coeffs"]); rm = np.ascontiguousarray(g["miss/ray"]); sm = np.ascontiguousarray(g["miss/source"])
+    akb._lib.check(L.akb_intersect_reflect_host(hp(co1), hp(rm), hp(sm), N, 0, hp(p), None, hp(r), hp(flags), -1), "host")
+    assert flags[0] == 1 and np.isnan(p).all() and np.isnan(r).all()   # ER3D:31-33
