@@ -6,7 +6,7 @@ from .wavecalc import (PHASE_EXACT, PHASE_FAITHFUL, WaveField3D, forward_propaga
                        forward_propagation_cupy_batch_multi_gpu, forward_propagation_numpy_batch,
                        fresnel_sum, fresnel_sum_sharded)
 from .raytrace import (PlanePoints, ell, intersect_reflect, mirr_ray_intersection, norm_vector,
-                       normalize_vector, plane_ray_intersection, reflect_ray, trace_chain)
+                       normalize_vector, plane_ray_intersection, reflect_ray, trace_chain, trace_chain_batched)
 from .handoff import calc_dS, opl_to_field
 from .psf import compute_psf_fft, field_to_pupil, psf_to_db
 from .stagechain import load_handoff, parse_conditions, run_stage_chain, write_handoff

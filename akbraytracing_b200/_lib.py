@@ -44,7 +44,8 @@ SIGNATURES = {
     "akb_plane_ray_intersection": (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp]),
     "akb_intersect_reflect": (_c_int, [_vp, _vp, _vp, _c_i64, _c_int, _vp, _vp, _vp, _c_uint, _vp, _vp]),
     "akb_trace_chain": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _c_uint, _vp, _vp]),
-    "akb_intersect_reflect_host": (_c_int, [_vp, _vp, _vp, _c_i64, _c_int, _vp, _vp, _vp, _vp, _c_int]),
+    "akb_trace_chain_batched": (_c_int, [_vp, _vp, _c_int, _vp, _c_int, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),
+    "akb_intersect_reflect_host":(_c_int, [_vp, _vp, _vp, _c_i64, _c_int, _vp, _vp, _vp, _vp, _c_int]),
     "akb_trace_chain_host": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int]),
     "akb_calc_ds": (_c_int, [_vp, _c_i64, _c_i64, _vp, _vp]),
     "akb_opl_to_field": (_c_int, [_vp, _vp, _c_i64, _c_dbl, _vp, _vp]),

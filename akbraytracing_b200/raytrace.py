@@ -23,7 +23,7 @@ import numpy as np
 from . import _lib
 
 __all__ = ["mirr_ray_intersection", "norm_vector", "reflect_ray", "normalize_vector",
-           "plane_ray_intersection", "intersect_reflect", "trace_chain", "ell", "PlanePoints",
+           "plane_ray_intersection", "intersect_reflect", "trace_chain", "trace_chain_batched", "ell", "PlanePoints",
            "Ell_define", "calcEll_Yvalue", "shift_x"]
 
 
@@ -211,6 +211,38 @@ def trace_chain(coeffs_list, negative_list, plane_coeffs, ray, source, want_norm
     o = lambda t: ctx.out(t) if t is not None else None  # noqa: E731
     return dict(points=o(pts), normals=o(nrm), reflects=o(rfl), last_reflect=o(last), det=o(det), dist=o(dist),
                 flags=flags)
+
+
+def trace_chain_batched(coeffs_batch, negative_list, planes_batch, ray, source, want_det=True):
+    """B geometries x one ray bundle in ONE launch (the auto_focus_NA scan pattern, BIG:12746-12895).
+
+    coeffs_batch: (B, K, 10); planes_batch: (B, 10); ray, source: (3, n) shared by all geometries.
+    Returns dict(det (B,3,n) or None, mean_y, std_y, mean_z, std_z (B,), miss (B,) int).  The std
+    is the population standard deviation the scans use (np.std(detcenter[1, :]), BIG:12786-12787);
+    like the reference's NaN fill, a geometry with missing rays gets NaN statistics."""
+    co = np.ascontiguousarray(np.asarray(coeffs_batch, dtype=np.float64))
+    if co.ndim != 3 or co.shape[2] != 10:
+        raise ValueError("coeffs_batch must have shape (B, K, 10)")
+    B, K = co.shape[0], co.shape[1]
+    planes = np.ascontiguousarray(np.asarray(planes_batch, dtype=np.float64).reshape(B, 10))
+    neg = np.ascontiguousarray(np.asarray([1 if b else 0 for b in negative_list], dtype=np.int32))
+    if neg.shape[0] != K:
+        raise ValueError("negative_list must have one entry per mirror")
+    ctx = _Ctx(ray, source)
+    r, s = ctx.rays(ray), ctx.rays(source)
+    n = r.shape[1]
+    det = ctx.empty(B, 3, n)
+    stats = ctx.empty(B, 4)
+    miss = ctx.torch.zeros(B, dtype=ctx.torch.int32, device=ctx.device)
+    _run(ctx, "akb_trace_chain_batched", _lib.host_ptr(co), _lib.host_ptr(neg), K, _lib.host_ptr(planes), B,
+         _lib.dev_ptr(r), _lib.dev_ptr(s), n, _lib.dev_ptr(det), _lib.dev_ptr(stats), _lib.dev_ptr(miss), ctx.stream)
+    bad = miss > 0
+    stats[bad] = float("nan")
+    if want_det:
+        det[bad] = float("nan")
+    o = ctx.out
+    return dict(det=o(det) if want_det else None, mean_y=o(stats[:, 0]), std_y=o(stats[:, 1]), mean_z=o(stats[:, 2]),
+                std_z=o(stats[:, 3]), miss=o(miss))
 
 
 # ---------------------------------------------------------------- ER3D's small host-side classes

@@ -150,6 +150,18 @@ int akb_trace_chain(const double *coeffs, const int *negative, int K, const doub
                     double *reflects, double *last_reflect, double *det, double *dist,
                     unsigned skip_normalize, int *flags, void *stream);
 
+/* B geometries (K quadrics + one plane each) trace the SAME ray bundle in one launch: the pattern of the
+ * focus / alignment scans auto_focus_NA (BIG:12746-12895: ~1600 calls of the tracer with 53x53 rays,
+ * each reduced to np.std of the detector y and z, BIG:12786-12787).
+ *   coeffs [B][K][10] (host), negative int[K] (host, shared), planes [B][10] (host)
+ *   ray, source [3][n] (device, shared by all geometries)
+ *   det   [B][3][n] (device)   detector points per geometry
+ *   stats [B][4] (device) or NULL: mean_y, std_y, mean_z, std_z of det (population std, like np.std)
+ *   miss  int[B] (device): rays with not(D > 0) per geometry */
+int akb_trace_chain_batched(const double *coeffs, const int *negative, int K, const double *planes, int B,
+                            const double *ray, const double *source, int64_t n, double *det, double *stats,
+                            int *miss, void *stream);
+
 /* Host-buffer forms (H2D, kernel, D2H, reference NaN-fill / all-or-nothing normalisation applied).
  * host_flags (int[AKB_NFLAGS], may be NULL) receives the raw flags of the last pass. */
 int akb_intersect_reflect_host(const double *coeffs, const double *ray, const double *source, int64_t N,

@@ -501,3 +501,36 @@ def test_intersect_reflect_host_abi(akb, golden):
     co1 = np.ascontiguousarray(g["single/coeffs"]); rm = np.ascontiguousarray(g["miss/ray"]); sm = np.ascontiguousarray(g["miss/source"])
     akb._lib.check(L.akb_intersect_reflect_host(hp(co1), hp(rm), hp(sm), N, 0, hp(p), None, hp(r), hp(flags), -1), "host")
     assert flags[0] == 1 and np.isnan(p).all() and np.isnan(r).all()   # ER3D:31-33
+
+
+def test_batched_small_traces_focus_scan(akb, torch):
+    """The auto_focus_NA pattern (BIG:12746-12895): many geometries x 53x53 rays in one launch, reduced
+    to np.std of the detector y / z.  Compared with one trace_chain call per geometry."""
+    from akbraytracing_b200 import workloads
+    from akbraytracing_b200.raytrace import shift_x
+    coeffs, neg, plane, ray, src = workloads.chain_inputs("c4", 53, "cuda")
+    B = 41
+    scan = np.linspace(-3e-4, 3e-4, B)               # defocus scan: the plane moves (params[0])
+    co_b = np.empty((B, 4, 10)); pl_b = np.empty((B, 10))
+    for b, a in enumerate(scan):
+        co_b[b] = coeffs
+        co_b[b, 3] = shift_x(list(coeffs[3]), 1e-7 * (b - B // 2))  # and the last mirror is nudged along x
+        pl_b[b] = plane
+        pl_b[b, 9] = plane[9] - a
+    out = akb.trace_chain_batched(co_b, neg, pl_b, ray, src)
+    assert out["det"].shape == (B, 3, 53 * 53) and int(out["miss"].sum()) == 0
+    for b in (0, 7, B // 2, B - 1):
+        one = akb.trace_chain(list(co_b[b]), neg, pl_b[b], ray, src)
+        assert torch.equal(out["det"][b], one["det"])           # same arithmetic, bit for bit
+        d = one["det"].cpu().numpy()
+        assert np.isclose(float(out["std_y"][b]), np.std(d[1]), rtol=1e-9, atol=0)   # BIG:12786-12787
+        assert np.isclose(float(out["std_z"][b]), np.std(d[2]), rtol=1e-9, atol=0)
+        assert np.isclose(float(out["mean_y"][b]), np.mean(d[1]), rtol=1e-12, atol=0)
+    # the scan has its focus inside the range: spot size is smallest near the nominal plane
+    sz = (out["std_y"] ** 2 + out["std_z"] ** 2).cpu().numpy()
+    assert 0 < int(np.argmin(sz)) < B - 1
+    # a geometry whose rays miss gets NaN statistics (reference: whole-array NaN)
+    co_bad = co_b.copy()
+    co_bad[3, 0, 9] = 1e6                              # first quadric of geometry 3 no longer intersects
+    bad = akb.trace_chain_batched(co_bad, neg, pl_b, ray, src, want_det=False)
+    assert int(bad["miss"][3]) > 0 and np.isnan(float(bad["std_y"][3])) and not np.isnan(float(bad["std_y"][2]))
