@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_PKG, "libakb_b200.so")
 
 PHASE_FAITHFUL = 0
 PHASE_EXACT = 1
+PHASE_REFERENCED = 2
 FLAG_MISS, FLAG_ZERO_NORM, FLAG_MISS_MASK, NFLAGS = 0, 1, 2, 4
 MAX_MIRRORS = 8
 

@@ -26,7 +26,9 @@ namespace {
 using namespace akb;
 
 constexpr int ROWS = 5; // sx, sy, sz, w_re, w_im
+constexpr int HEAD = 4; // per-tile header after the rows: reference point c_T (x, y, z) + pad
 constexpr int THREADS = 256;
+constexpr int AKB_PHASE_REFERENCED_ = AKB_PHASE_REFERENCED;
 
 struct PhaseConst {
     double k;        // FAITHFUL: phase = fl(k * r)
@@ -42,7 +44,7 @@ struct PhaseConst {
 __global__ void pack_sources_kernel(const double *__restrict__ sx, const double *__restrict__ sy,
                                     const double *__restrict__ sz, const double *__restrict__ u,
                                     const double *__restrict__ ds, long long N, long long padded, int tile,
-                                    double *__restrict__ packed)
+                                    int relative, double *__restrict__ packed)
 {
     long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= padded) return;
@@ -57,12 +59,22 @@ __global__ void pack_sources_kernel(const double *__restrict__ sx, const double 
     }
     long long t_idx = j / tile;
     int o = (int)(j % tile);
-    double *t = packed + t_idx * (long long)(ROWS * tile);
-    t[0 * tile + o] = sx[jj];
-    t[1 * tile + o] = sy[jj];
-    t[2 * tile + o] = sz[jj];
+    double *t = packed + t_idx * (long long)(ROWS * tile + HEAD);
+    // reference point of the tile = its first source; REFERENCED mode stores the sources relative to it
+    // (differences of nearby points: exact or within 1e-18 m)
+    const long long jc = t_idx * tile < N ? t_idx * tile : N - 1;
+    const double cx = sx[jc], cy = sy[jc], cz = sz[jc];
+    t[0 * tile + o] = relative ? sub(sx[jj], cx) : sx[jj];
+    t[1 * tile + o] = relative ? sub(sy[jj], cy) : sy[jj];
+    t[2 * tile + o] = relative ? sub(sz[jj], cz) : sz[jj];
     t[3 * tile + o] = wr;
     t[4 * tile + o] = wi;
+    if (o == 0) {
+        t[ROWS * tile + 0] = cx;
+        t[ROWS * tile + 1] = cy;
+        t[ROWS * tile + 2] = cz;
+        t[ROWS * tile + 3] = 0.0;
+    }
 }
 
 // ---------------------------------------------------------------- mbarrier / TMA bulk helpers
@@ -120,10 +132,99 @@ __constant__ double KC[KC_COUNT] = {
 // The 2*DPT pairs of one loop iteration go through the phases together, which puts the table load
 // of a pair ~40 FP64 instructions ahead of its use.
 struct PairA {
-    double p; // FAITHFUL: fl(k*r); EXACT: r
+    double p; // FAITHFUL: fl(k*r); EXACT: r; REFERENCED: r - r_ref
     double h; // 1/(2r)
     double t; // MAGIC + rint(phase / u); its low word is the table index
 };
+
+// ---- REFERENCED mode: optical path relative to a per-tile reference point -------------------------
+// r_ij is never formed as one double (its rounding alone is k*ulp(r)/2 = 7e-5 rad at 146 m, 1.35 nm).
+// For detector point d and the reference point c of a source tile,  D = d - c  and  r_ref = |D|  are
+// evaluated once per (detector, tile) in double-double; for a source s_j = c + e_j of the tile
+//     r_ij^2 - r_ref^2 = sum_c e_c (e_c - 2 D_c) =: ds          (small numbers, full relative precision)
+//     r_ij   - r_ref   = ds / (sqrt(r_ref^2 + ds) + r_ref)      (one correctly rounded quotient)
+// so the path difference carries 1 ulp of ITSELF (<= 2e-18 m for a 15 mm tile), and the phase is
+// (k r_ref mod 2 pi, held per (detector, tile) with ~1e-10 rad) + k (r_ij - r_ref) reduced exactly.
+struct RefCtx {
+    double gx, gy, gz; // -2 D (high words)
+    double s_ref;      // |D|^2 (high word)
+    double r_ref;      // |D|   (high word)
+    double phi;        // frac(k r_ref / u) in [-1/2, 1/2], from the double-double value
+    int n_ref;         // rint(k r_ref / u) mod 2^32
+};
+
+__device__ __forceinline__ void two_sum(double a, double b, double &s, double &e)
+{
+    s = add(a, b);
+    const double bb = sub(s, a);
+    e = add(sub(a, sub(s, bb)), sub(b, bb));
+}
+
+__device__ __forceinline__ RefCtx make_ref_ctx(double X, double Y, double Z, double cx, double cy, double cz,
+                                               const PhaseConst &pc, double magic)
+{
+    double dh[3], dl[3];
+    two_sum(X, -cx, dh[0], dl[0]); // D = d - c exactly as hi + lo
+    two_sum(Y, -cy, dh[1], dl[1]);
+    two_sum(Z, -cz, dh[2], dl[2]);
+    double sh = 0.0, sl = 0.0; // |D|^2 in double-double
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double p = mul(dh[c], dh[c]);
+        const double pe = fma_(dh[c], dh[c], -p) + 2.0 * dh[c] * dl[c];
+        double s1, e1;
+        two_sum(sh, p, s1, e1);
+        sh = s1;
+        sl = sl + e1 + pe;
+    }
+    two_sum(sh, sl, sh, sl);
+    RefCtx r;
+    r.gx = -2.0 * dh[0];
+    r.gy = -2.0 * dh[1];
+    r.gz = -2.0 * dh[2];
+    r.s_ref = sh;
+    double r0 = __dsqrt_rn(sh), rl = 0.0;
+    if (r0 > 0.0) rl = __ddiv_rn(fma_(-r0, r0, sh) + sl, 2.0 * r0); // sqrt(sh + sl) = r0 + rl
+    r.r_ref = r0;
+    // k r_ref / u = n_ref + phi with (r0 + rl) * (q_hi + q_lo)
+    const double t0 = fma_(r0, pc.q_hi, magic);
+    const double n0 = add(t0, KC[KC_NEG_MAGIC]);
+    double phi = fma_(r0, pc.q_hi, -n0);
+    phi = fma_(r0, pc.q_lo, phi);
+    phi = fma_(rl, pc.q_hi, phi);
+    r.phi = phi;
+    r.n_ref = __double2loint(t0);
+    return r;
+}
+
+// MUFU.RCP64H + 2 Newton steps: 1/b to < 1 ulp
+__device__ __forceinline__ double rcp_refined(double b)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    double e = fma_(-b, y, 1.0);
+    y = fma_(y, e, y);
+    e = fma_(-b, y, 1.0);
+    return fma_(y, e, y);
+}
+
+// phase A of a REFERENCED pair: (ex, ey, ez) = source - tile reference
+__device__ __forceinline__ PairA pair_phase_a_ref(const RefCtx &rc, double ex, double ey, double ez,
+                                                  const PhaseConst &pc, double magic)
+{
+    const double ax = add(ex, rc.gx), ay = add(ey, rc.gy), az = add(ez, rc.gz);
+    const double ds = fma_(ex, ax, fma_(ey, ay, mul(ez, az))); // r^2 - r_ref^2
+    const double s = add(rc.s_ref, ds);
+    PairA a;
+    double rho;
+    sqrt_and_half_rinv(s, rho, a.h);
+    const double den = add(rho, rc.r_ref);
+    const double y = rcp_refined(den);
+    const double q = mul(ds, y);
+    a.p = fma_(fma_(-den, q, ds), y, q);                     // r - r_ref, correctly rounded quotient
+    a.t = add(fma_(a.p, pc.q_hi, rc.phi), magic);            // MAGIC + rint((k (r - r_ref))/u + phi)
+    return a;
+}
 
 template <int MODE>
 __device__ __forceinline__ PairA pair_phase_a(double X, double Y, double Z, double sx, double sy, double sz,
@@ -169,13 +270,19 @@ __device__ __forceinline__ double2 lds_double2(uint32_t addr)
 // exact Cody-Waite reduction + h*(cos f, sin f): n = rint(p/u), f = p - n*u.  fma(n, -u_hi, p) is
 // exact (the difference fits in 53 bits); the u_lo term restores the bits of u beyond double.
 template <int MODE, int TBL>
-__device__ __forceinline__ void pair_phase_b(const PairA &a, const PhaseConst &pc, double t2, double &cf, double &sf)
+__device__ __forceinline__ void pair_phase_b(const PairA &a, const PhaseConst &pc, double t2, double phi, double &cf,
+                                             double &sf)
 {
     const double n = add(a.t, KC[KC_NEG_MAGIC]);
     double f;
     if (MODE == AKB_PHASE_FAITHFUL) {
         f = fma_(n, pc.neg_u_hi, a.p);
         f = fma_(n, pc.neg_u_lo, f);
+    } else if (MODE == AKB_PHASE_REFERENCED_) {
+        f = fma_(a.p, pc.q_hi, -n); // exact: (r - r_ref) q_hi - n fits in 53 bits
+        f = add(f, phi);
+        f = fma_(a.p, pc.q_lo, f);
+        f = mul(f, pc.u);
     } else {
         f = fma_(a.p, pc.q_hi, -n);
         f = fma_(a.p, pc.q_lo, f);
@@ -214,7 +321,7 @@ __device__ __forceinline__ void pair_phase_c(double2 cs, double cf, double sf, d
 // out: [gridDim.y][M] complex partial sums (gridDim.y == 1 -> the result itself).
 template <int TILE, int STAGES, int TBL>
 struct PairCfg {
-    static constexpr int kTileBytes = ROWS * TILE * 8;
+    static constexpr int kTileBytes = (ROWS * TILE + HEAD) * 8; // rows + the tile's reference point
     static constexpr int kTableBytes = TBL * 16;
     // tiles | mbarriers | 2 loop constants | table (aligned to its own size: that much slack)
     static constexpr int kSmemBytes = STAGES * kTileBytes + STAGES * 8 + 16 + 2 * kTableBytes;
@@ -227,7 +334,8 @@ __global__ void __launch_bounds__(THREADS) fresnel_pairs_kernel(
     const __grid_constant__ PhaseConst pc, double *__restrict__ out)
 {
     using Cfg = PairCfg<TILE, STAGES, TBL>;
-    constexpr int TILE_DOUBLES = ROWS * TILE;
+    constexpr int TILE_DOUBLES = ROWS * TILE + HEAD;
+    constexpr bool REF = MODE == AKB_PHASE_REFERENCED_;
     constexpr int NP = 2 * DPT; // pairs per loop iteration: DPT detector points x 2 sources
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *tiles = reinterpret_cast<double *>(smem_raw);
@@ -287,6 +395,12 @@ __global__ void __launch_bounds__(THREADS) fresnel_pairs_kernel(
         const double *T = tiles + stage * TILE_DOUBLES;
         const long long left = n_padded - (long long)t * TILE;
         const int cnt = left < TILE ? (int)left : TILE; // multiple of 2
+        RefCtx rc[REF ? DPT : 1];
+        if (REF) { // once per (detector point, tile): double-double distance to the tile's reference point
+#pragma unroll
+            for (int d = 0; d < DPT; ++d)
+                rc[d] = make_ref_ctx(X[d], Y[d], Z[d], T[ROWS * TILE + 0], T[ROWS * TILE + 1], T[ROWS * TILE + 2], pc, magic);
+        }
 #pragma unroll 1
         for (int j = 0; j < cnt; j += 2) {
             const double2 vx = *reinterpret_cast<const double2 *>(T + 0 * TILE + j);
@@ -299,13 +413,19 @@ __global__ void __launch_bounds__(THREADS) fresnel_pairs_kernel(
             double cf[NP], sf[NP];
 #pragma unroll
             for (int d = 0; d < DPT; ++d) {
-                a[2 * d] = pair_phase_a<MODE>(X[d], Y[d], Z[d], vx.x, vy.x, vz.x, pc, magic);
-                cs[2 * d] = lds_double2(table_slot<TBL, SWZ>(__double2loint(a[2 * d].t), table_s));
-                a[2 * d + 1] = pair_phase_a<MODE>(X[d], Y[d], Z[d], vx.y, vy.y, vz.y, pc, magic);
-                cs[2 * d + 1] = lds_double2(table_slot<TBL, SWZ>(__double2loint(a[2 * d + 1].t), table_s));
+                if (REF) {
+                    a[2 * d] = pair_phase_a_ref(rc[d], vx.x, vy.x, vz.x, pc, magic);
+                    a[2 * d + 1] = pair_phase_a_ref(rc[d], vx.y, vy.y, vz.y, pc, magic);
+                } else {
+                    a[2 * d] = pair_phase_a<MODE>(X[d], Y[d], Z[d], vx.x, vy.x, vz.x, pc, magic);
+                    a[2 * d + 1] = pair_phase_a<MODE>(X[d], Y[d], Z[d], vx.y, vy.y, vz.y, pc, magic);
+                }
+                const int n_ref = REF ? rc[d].n_ref : 0; // table index = n_ref + rint(k (r - r_ref)/u + phi)
+                cs[2 * d] = lds_double2(table_slot<TBL, SWZ>(__double2loint(a[2 * d].t) + n_ref, table_s));
+                cs[2 * d + 1] = lds_double2(table_slot<TBL, SWZ>(__double2loint(a[2 * d + 1].t) + n_ref, table_s));
             }
 #pragma unroll
-            for (int i = 0; i < NP; ++i) pair_phase_b<MODE, TBL>(a[i], pc, t2, cf[i], sf[i]);
+            for (int i = 0; i < NP; ++i) pair_phase_b<MODE, TBL>(a[i], pc, t2, REF ? rc[i / 2].phi : 0.0, cf[i], sf[i]);
             // phase C: rotate by the table entry, then accumulate.  The accumulation is ordered by
             // source and by operation so that consecutive DFMAs share their first operand (w_re or
             // w_im of one source): served by the operand-reuse cache, they read 2 registers, not 3.
@@ -404,7 +524,7 @@ PhaseConst make_phase_const(double k, int table)
 struct KernelEntry {
     const char *name;
     int dpt, tile, stages, table;
-    const void *fn[2]; // per mode
+    const void *fn[3]; // per mode
     int smem;
 };
 
@@ -419,6 +539,7 @@ KernelEntry make_entry(const char *name)
     e.table = TBL;
     e.fn[0] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_FAITHFUL, TILE, STAGES, TBL, SWZ>);
     e.fn[1] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_EXACT, TILE, STAGES, TBL, SWZ>);
+    e.fn[2] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_REFERENCED, TILE, STAGES, TBL, SWZ>);
     e.smem = PairCfg<TILE, STAGES, TBL>::kSmemBytes;
     return e;
 }
@@ -437,17 +558,19 @@ const KernelEntry *kernel_table(int *count)
     return entries;
 }
 
-const KernelEntry &selected_kernel()
+const KernelEntry &selected_kernel(int mode)
 {
     int n = 0;
     const KernelEntry *e = kernel_table(&n);
-    static int idx = -1;
-    if (idx < 0) {
+    static int idx = -1; // -1: not read yet, -2: no override
+    if (idx == -1) {
         const char *v = getenv("AKB_FRESNEL_VARIANT");
-        int want = v ? atoi(v) : 0;
-        idx = (want >= 0 && want < n) ? want : 0;
+        int want = v ? atoi(v) : -2;
+        idx = (want >= 0 && want < n) ? want : -2;
     }
-    return e[idx];
+    if (idx >= 0) return e[idx];
+    // REFERENCED keeps 7 more doubles per detector point in registers: 2 points per thread
+    return e[mode == AKB_PHASE_REFERENCED ? 1 : 0];
 }
 
 // optional in-library timing of the last akb_fresnel_sum call of this thread (bench.py roofline)
@@ -486,7 +609,8 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
                                int mode, void *stream)
 {
     AKB_REQUIRE(M >= 0 && N >= 0, "M and N must be non-negative");
-    AKB_REQUIRE(mode == AKB_PHASE_FAITHFUL || mode == AKB_PHASE_EXACT, "mode must be AKB_PHASE_FAITHFUL or AKB_PHASE_EXACT");
+    AKB_REQUIRE(mode == AKB_PHASE_FAITHFUL || mode == AKB_PHASE_EXACT || mode == AKB_PHASE_REFERENCED,
+                "mode must be AKB_PHASE_FAITHFUL, AKB_PHASE_EXACT or AKB_PHASE_REFERENCED");
     if (M == 0) return AKB_OK;
     AKB_REQUIRE(det_x && det_y && det_z && out, "detector/out pointers must not be NULL");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -502,7 +626,7 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     AKB_CUDA(cudaGetDevice(&device));
     tune_pool(device);
     const int sms = sm_count(device);
-    const KernelEntry &ke = selected_kernel();
+    const KernelEntry &ke = selected_kernel(mode);
     const void *kern = ke.fn[mode];
     const int TILE = ke.tile;
 
@@ -547,11 +671,12 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     if ((rc = timing_mark(0, st))) return rc;
 
     double *packed = nullptr, *partial = nullptr;
-    AKB_CUDA(cudaMallocAsync(&packed, (size_t)padded * ROWS * sizeof(double), st));
+    AKB_CUDA(cudaMallocAsync(&packed, (size_t)tiles_total * (ROWS * TILE + HEAD) * sizeof(double), st));
     if (splits > 1) AKB_CUDA(cudaMallocAsync(&partial, (size_t)splits * M * 2 * sizeof(double), st));
 
     pack_sources_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, st>>>(src_x, src_y, src_z, src_u, src_ds, N,
-                                                                          padded, TILE, packed);
+                                                                          padded, TILE,
+                                                                          mode == AKB_PHASE_REFERENCED ? 1 : 0, packed);
     AKB_LAUNCH_CHECK();
 
     PhaseConst pc = make_phase_const(k, ke.table);
@@ -603,7 +728,7 @@ extern "C" int akb_fresnel_last_timing(double *pairs_ms, double *total_ms, int *
     return AKB_OK;
 }
 
-extern "C" const char *akb_fresnel_variant_name(void) { return selected_kernel().name; }
+extern "C" const char *akb_fresnel_variant_name(void) { return selected_kernel(AKB_PHASE_FAITHFUL).name; }
 
 extern "C" int akb_fresnel_sum_host(const double *det_x, const double *det_y, const double *det_z, int64_t M,
                                     const double *src_x, const double *src_y, const double *src_z,

@@ -18,11 +18,11 @@ import time
 import numpy as np
 
 from . import _lib
-from ._lib import PHASE_EXACT, PHASE_FAITHFUL  # noqa: F401  (re-exported)
+from ._lib import PHASE_EXACT, PHASE_FAITHFUL, PHASE_REFERENCED  # noqa: F401  (re-exported)
 
 __all__ = ["WaveField3D", "forward_propagation_numpy_batch", "forward_propagation_cupy_batch",
            "forward_propagation_cupy_batch_multi_gpu", "fresnel_sum", "fresnel_sum_sharded",
-           "PHASE_FAITHFUL", "PHASE_EXACT"]
+           "PHASE_FAITHFUL", "PHASE_EXACT", "PHASE_REFERENCED"]
 
 
 def _any_torch(*arrays) -> bool:

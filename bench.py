@@ -317,7 +317,10 @@ def run_ours(args):
         roofline = {
             "kernel": "fresnel_pairs_kernel<faithful> [%s]" % L.akb_fresnel_variant_name().decode(), "bound": "fp64",
             "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of THIS launch (1e6 sources x 512x512 detectors,
+            # 8 source splits) from ncu --set full: profiles/r01_ncu_full_bench_launch.md (48.1 MB + 8.9 MB).
+            # Algorithmic bytes: 40 MB packed sources + 6.3 MB detector xyz + 33.5 MB partial sums.
+            "traffic": 57.0e6 if world == 1 else None, "traffic_unit": "bytes per launch (ncu, round 1)",
             "peak_source": "on-box DFMA microbenchmark (akb_fp64_peak_probe, measured in this run); "
                            "MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
             "algorithmic_flop_per_term": ALG_FLOP_PER_TERM,

@@ -38,6 +38,8 @@ extern "C" {
 #define AKB_PHASE_FAITHFUL 0 /* r and k*r rounded exactly like NumPy/numba (default) */
 #define AKB_PHASE_EXACT 1    /* fused r^2; the product k*r is never rounded (reduced in quarter \
                                 turns); r itself is still one rounded double */
+#define AKB_PHASE_REFERENCED 2 /* optical path relative to a per-tile reference point: r is never \
+                                  rounded as a whole, phases keep ~1e-8 rad even at k*r ~ 1e12 */
 
 /* entries of the int[AKB_NFLAGS] status block written by the ray kernels */
 #define AKB_FLAG_MISS 0      /* number of rays with not(D > 0)                  ER3D:31 */
@@ -69,7 +71,7 @@ int akb_device_count(void);
  *   src_u      complex128[N]  field on the back surface, (re,im) interleaved
  *   src_ds     float64[N] or NULL (= 1)
  *   out        complex128[M]
- *   mode       AKB_PHASE_FAITHFUL | AKB_PHASE_EXACT
+ *   mode       AKB_PHASE_FAITHFUL | AKB_PHASE_EXACT | AKB_PHASE_REFERENCED
  */
 int akb_fresnel_sum(const double *det_x, const double *det_y, const double *det_z, int64_t M,
                     const double *src_x, const double *src_y, const double *src_z,
