@@ -69,5 +69,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def ensure_built() -> str:
+    """Build if the library is missing or older than its sources; safe to call from several ranks
+    at once (an exclusive file lock serialises them, late comers find the library up to date).
+    Used by tests, bench.py and __graft_entry__ -- the product import path never builds implicitly."""
+    import fcntl
+    if not needs_build():
+        return LIB
+    os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
+    with open(os.path.join(PKG, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return build()
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

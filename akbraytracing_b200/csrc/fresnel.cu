@@ -11,10 +11,12 @@
 //     streams source tiles through an mbarrier ring;
 //   * per pair: r = sqrt(dx^2+dy^2+dz^2) from one MUFU.RSQ64H + 7 FP64 ops (correctly rounded,
 //     also yields 1/(2r)), the phase k*r reduced EXACTLY (Cody-Waite with FMA) to a multiple of
-//     2*pi/512 plus a remainder |f| <= pi/512, exp(-i f) from a 2-term polynomial, and the
-//     multiple looked up in a 512-entry (cos, sin) table in shared memory: 36 FP64-pipe
-//     instructions and ~8 others per pair, no libdevice sincos (its Payne-Hanek slow path is
+//     2*pi/1024 plus a remainder |f| <= pi/1024, exp(-i f) from a short polynomial, and the
+//     multiple looked up in a 1024-entry (cos, sin) table in shared memory: 35 FP64-pipe
+//     instructions and ~6 others per pair, no libdevice sincos (its Payne-Hanek slow path is
 //     unusable at k*r ~ 1e9);
+//   * three phase modes: FAITHFUL (NumPy/numba rounding, the parity default), EXACT (k*r never
+//     rounded), REFERENCED (optical path relative to a per-tile reference point);
 //   * bound: FP64 ALU (DFMA pipe, 64 lanes/SM).  HBM traffic is 40 B per source per
 //     detector block, i.e. ~0 B per pair; there is no dense contraction, so no tensor cores.
 #include <stdlib.h>
@@ -28,7 +30,6 @@ using namespace akb;
 constexpr int ROWS = 5; // sx, sy, sz, w_re, w_im
 constexpr int HEAD = 4; // per-tile header after the rows: reference point c_T (x, y, z) + pad
 constexpr int THREADS = 256;
-constexpr int AKB_PHASE_REFERENCED_ = AKB_PHASE_REFERENCED;
 
 struct PhaseConst {
     double k;        // FAITHFUL: phase = fl(k * r)
@@ -278,7 +279,7 @@ __device__ __forceinline__ void pair_phase_b(const PairA &a, const PhaseConst &p
     if (MODE == AKB_PHASE_FAITHFUL) {
         f = fma_(n, pc.neg_u_hi, a.p);
         f = fma_(n, pc.neg_u_lo, f);
-    } else if (MODE == AKB_PHASE_REFERENCED_) {
+    } else if (MODE == AKB_PHASE_REFERENCED) {
         f = fma_(a.p, pc.q_hi, -n); // exact: (r - r_ref) q_hi - n fits in 53 bits
         f = add(f, phi);
         f = fma_(a.p, pc.q_lo, f);
@@ -301,20 +302,8 @@ __device__ __forceinline__ void pair_phase_b(const PairA &a, const PhaseConst &p
     cf = mul(a.h, c1);
 }
 
-// rotate by the tabulated multiple (C, S) = (cos, sin)(2*pi*m/TBL) and accumulate
-// (wr + i wi) * (c - i sn)   [exp(-i k r)/r, CPU0402:81-84]
-__device__ __forceinline__ void pair_phase_c(double2 cs, double cf, double sf, double wr, double wi, double &acc_re,
-                                             double &acc_im)
-{
-    const double m1 = mul(cs.x, cf);
-    const double m2 = mul(cs.y, cf);
-    const double c = fma_(-cs.y, sf, m1);
-    const double sn = fma_(cs.x, sf, m2);
-    acc_re = fma_(wr, c, acc_re);
-    acc_im = fma_(wi, c, acc_im);
-    acc_re = fma_(wi, sn, acc_re);
-    acc_im = fma_(-wr, sn, acc_im);
-}
+// Phase C -- rotate by the tabulated multiple (C, S) = (cos, sin)(2*pi*m/TBL) and accumulate
+// (wr + i wi) * (c - i sn)   [exp(-i k r)/r, CPU0402:81-84] -- is written out in the kernel loop.
 
 // ---------------------------------------------------------------- pair kernel
 // grid.x: blocks of THREADS*DPT detector points; grid.y: splits of the source tiles.
@@ -335,7 +324,7 @@ __global__ void __launch_bounds__(THREADS) fresnel_pairs_kernel(
 {
     using Cfg = PairCfg<TILE, STAGES, TBL>;
     constexpr int TILE_DOUBLES = ROWS * TILE + HEAD;
-    constexpr bool REF = MODE == AKB_PHASE_REFERENCED_;
+    constexpr bool REF = MODE == AKB_PHASE_REFERENCED;
     constexpr int NP = 2 * DPT; // pairs per loop iteration: DPT detector points x 2 sources
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *tiles = reinterpret_cast<double *>(smem_raw);

@@ -197,6 +197,8 @@ def workload_config(n_gpus):
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    from akbraytracing_b200 import build as akb_build
+    akb_build.ensure_built()  # no-op when the in-tree library is current; ranks serialise on a file lock
     import akbraytracing_b200 as akb
     from akbraytracing_b200 import handoff, raytrace, workloads, _lib
     import ctypes

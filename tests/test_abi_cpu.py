@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.fixture(scope="module")
 def lib():
     from akbraytracing_b200 import build, _lib
-    build.build()
+    build.ensure_built()
     return _lib.load()
 
 

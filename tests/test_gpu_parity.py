@@ -22,6 +22,8 @@ RAY_TOL = 1e-12   # north_star: ray hit points and directions within 1e-12 relat
 def akb():
     import torch
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from akbraytracing_b200 import build
+    build.ensure_built()  # no-op when the in-tree libakb_b200.so is up to date
     import akbraytracing_b200 as pkg
     pkg._lib.load()
     return pkg
