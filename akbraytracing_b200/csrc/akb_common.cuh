@@ -13,6 +13,8 @@ void count_launch(int n = 1);
 int sm_count(int device);
 // make the stream-ordered pool of `device` keep its memory between calls (once per device)
 void tune_pool(int device);
+// cached non-blocking stream of the calling host thread on `device` (nullptr on failure)
+cudaStream_t host_stream(int device);
 
 #define AKB_CUDA(expr)                                                                         \
     do {                                                                                       \

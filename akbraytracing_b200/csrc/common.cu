@@ -48,6 +48,18 @@ void tune_pool(int device)
     g_pool_tuned[device] = true;
 }
 
+// One non-blocking stream per (host thread, device) for the synchronous "_host" entry points:
+// creating and destroying a stream per call costs more than a C1-sized problem takes to compute.
+cudaStream_t host_stream(int device)
+{
+    static thread_local cudaStream_t streams[64] = {};
+    if (device < 0 || device >= 64) return nullptr;
+    if (!streams[device]) {
+        if (cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking) != cudaSuccess) streams[device] = nullptr;
+    }
+    return streams[device];
+}
+
 } // namespace akb
 
 extern "C" const char *akb_last_error(void) { return akb::g_error; }

@@ -547,7 +547,7 @@ const KernelEntry *kernel_table(int *count)
     return entries;
 }
 
-const KernelEntry &selected_kernel(int mode)
+const KernelEntry &selected_kernel(int mode, long long M = -1, long long N = -1, int sms = 148)
 {
     int n = 0;
     const KernelEntry *e = kernel_table(&n);
@@ -559,7 +559,19 @@ const KernelEntry &selected_kernel(int mode)
     }
     if (idx >= 0) return e[idx];
     // REFERENCED keeps 7 more doubles per detector point in registers: 2 points per thread
-    return e[mode == AKB_PHASE_REFERENCED ? 1 : 0];
+    int pick = mode == AKB_PHASE_REFERENCED ? 1 : 0;
+    // small problems (C1: 64x64 detector points x 1e4 sources): fewer points per thread so that
+    // (detector blocks x source tiles) still covers every SM
+    if (M >= 0 && N >= 0) {
+        const int order[3] = {pick, 1, 3}; // 4 (or 2), 2, 1 points per thread
+        for (int o = 0; o < 3; ++o) {
+            pick = order[o];
+            const long long blocks = (M + THREADS * e[pick].dpt - 1) / (THREADS * e[pick].dpt);
+            const long long tiles = (N + e[pick].tile - 1) / e[pick].tile;
+            if (blocks * tiles >= 2LL * sms || e[pick].dpt == 1) break;
+        }
+    }
+    return e[pick];
 }
 
 // optional in-library timing of the last akb_fresnel_sum call of this thread (bench.py roofline)
@@ -615,7 +627,7 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     AKB_CUDA(cudaGetDevice(&device));
     tune_pool(device);
     const int sms = sm_count(device);
-    const KernelEntry &ke = selected_kernel(mode);
+    const KernelEntry &ke = selected_kernel(mode, M, N, sms);
     const void *kern = ke.fn[mode];
     const int TILE = ke.tile;
 
@@ -731,8 +743,8 @@ extern "C" int akb_fresnel_sum_host(const double *det_x, const double *det_y, co
     if (device >= 0) AKB_CUDA(cudaSetDevice(device)); // device < 0: the calling thread's current device
     AKB_CUDA(cudaGetDevice(&device));
     tune_pool(device);
-    cudaStream_t st;
-    AKB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaStream_t st = host_stream(device);
+    AKB_REQUIRE(st != nullptr, "could not create a stream on the device");
     const size_t mb = (size_t)M * sizeof(double), nb = (size_t)(N > 0 ? N : 1) * sizeof(double);
     double *d = nullptr;
     // one slab: out (2M) | u (2N) | det xyz (3M) | src xyz (3N) | ds (N); the two complex arrays
@@ -742,7 +754,6 @@ extern "C" int akb_fresnel_sum_host(const double *det_x, const double *det_y, co
     cudaError_t e = cudaMallocAsync(&d, total, st);
     if (e != cudaSuccess) {
         set_error("cudaMallocAsync(%zu) failed: %s", total, cudaGetErrorString(e));
-        cudaStreamDestroy(st);
         return AKB_ERR_CUDA;
     }
     const int64_t Nn = N > 0 ? N : 1;
@@ -772,7 +783,6 @@ extern "C" int akb_fresnel_sum_host(const double *det_x, const double *det_y, co
         set_error("stream synchronize failed: %s", cudaGetErrorString(e));
         rc = AKB_ERR_CUDA;
     }
-    cudaStreamDestroy(st);
     return rc;
 }
 
