@@ -250,14 +250,14 @@ __device__ __forceinline__ PairA pair_phase_a(double X, double Y, double Z, doub
 }
 
 // Byte address of table entry (q mod TBL).  The table is aligned to its own size, so the index bits
-// can be OR-ed into the base with one LOP3.  SWZ additionally XORs the 16-byte bank-group bits with
-// index bits 3..5, which spreads power-of-two index strides across the lanes of a warp.
-template <int TBL, bool SWZ>
+// can be OR-ed into the base with one LOP3.  (An XOR swizzle of the bank-group bits that spreads
+// power-of-two index strides across the lanes was measured: its two extra ALU instructions per pair
+// cost more issue slots than the bank conflicts it removes, 442 vs 449 Gterms/s on C3.)
+template <int TBL>
 __device__ __forceinline__ uint32_t table_slot(int q, uint32_t table_s)
 {
     uint32_t addr;
-    const int qs = SWZ ? (q ^ ((q >> 3) & 7)) : q;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(addr) : "r"(qs << 4), "n"((TBL - 1) << 4), "r"(table_s));
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(addr) : "r"(q << 4), "n"((TBL - 1) << 4), "r"(table_s));
     return addr;
 }
 
@@ -316,8 +316,8 @@ struct PairCfg {
     static constexpr int kSmemBytes = STAGES * kTileBytes + STAGES * 8 + 16 + 2 * kTableBytes;
 };
 
-template <int DPT, int MODE, int TILE, int STAGES, int TBL, bool SWZ>
-__global__ void __launch_bounds__(THREADS) fresnel_pairs_kernel(
+template <int DPT, int MODE, int TILE, int STAGES, int TBL, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
     const double *__restrict__ det_x, const double *__restrict__ det_y, const double *__restrict__ det_z,
     long long M, const double *__restrict__ packed, int tiles_total, int tiles_per_split, long long n_padded,
     const __grid_constant__ PhaseConst pc, double *__restrict__ out)
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(THREADS) fresnel_pairs_kernel(
     for (int m = threadIdx.x; m < TBL; m += THREADS) {
         double sv, cv;
         sincospi((double)m * (2.0 / TBL), &sv, &cv); // exact argument: accurate to < 1 ulp
-        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(table_slot<TBL, SWZ>(m, table_s)), "d"(cv), "d"(sv) : "memory");
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(table_slot<TBL>(m, table_s)), "d"(cv), "d"(sv) : "memory");
     }
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -410,8 +410,8 @@ __global__ void __launch_bounds__(THREADS) fresnel_pairs_kernel(
                     a[2 * d + 1] = pair_phase_a<MODE>(X[d], Y[d], Z[d], vx.y, vy.y, vz.y, pc, magic);
                 }
                 const int n_ref = REF ? rc[d].n_ref : 0; // table index = n_ref + rint(k (r - r_ref)/u + phi)
-                cs[2 * d] = lds_double2(table_slot<TBL, SWZ>(__double2loint(a[2 * d].t) + n_ref, table_s));
-                cs[2 * d + 1] = lds_double2(table_slot<TBL, SWZ>(__double2loint(a[2 * d + 1].t) + n_ref, table_s));
+                cs[2 * d] = lds_double2(table_slot<TBL>(__double2loint(a[2 * d].t) + n_ref, table_s));
+                cs[2 * d + 1] = lds_double2(table_slot<TBL>(__double2loint(a[2 * d + 1].t) + n_ref, table_s));
             }
 #pragma unroll
             for (int i = 0; i < NP; ++i) pair_phase_b<MODE, TBL>(a[i], pc, t2, REF ? rc[i / 2].phi : 0.0, cf[i], sf[i]);
@@ -517,7 +517,7 @@ struct KernelEntry {
     int smem;
 };
 
-template <int DPT, int TILE, int STAGES, int TBL, bool SWZ>
+template <int DPT, int TILE, int STAGES, int TBL, int MINB>
 KernelEntry make_entry(const char *name)
 {
     KernelEntry e;
@@ -526,22 +526,23 @@ KernelEntry make_entry(const char *name)
     e.tile = TILE;
     e.stages = STAGES;
     e.table = TBL;
-    e.fn[0] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_FAITHFUL, TILE, STAGES, TBL, SWZ>);
-    e.fn[1] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_EXACT, TILE, STAGES, TBL, SWZ>);
-    e.fn[2] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_REFERENCED, TILE, STAGES, TBL, SWZ>);
+    e.fn[0] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_FAITHFUL, TILE, STAGES, TBL, MINB>);
+    e.fn[1] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_EXACT, TILE, STAGES, TBL, MINB>);
+    e.fn[2] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_REFERENCED, TILE, STAGES, TBL, MINB>);
     e.smem = PairCfg<TILE, STAGES, TBL>::kSmemBytes;
     return e;
 }
 
-// Tuning variants; index 0 is the default.  AKB_FRESNEL_VARIANT=<n> selects another one.
+// Kernel variants: <points per thread, tile, stages, table entries, min resident blocks/SM>.
+// Entries 0, 1, 3 are used by the size-aware default choice; AKB_FRESNEL_VARIANT=<n> forces one.
 const KernelEntry *kernel_table(int *count)
 {
     static const KernelEntry entries[] = {
-        make_entry<4, 512, 2, 1024, false>("dpt4 tile512x2 table1024"),
-        make_entry<2, 512, 2, 1024, false>("dpt2 tile512x2 table1024"),
-        make_entry<4, 512, 2, 512, false>("dpt4 tile512x2 table512"),
-        make_entry<1, 512, 2, 1024, false>("dpt1 tile512x2 table1024"),
-        make_entry<4, 512, 2, 1024, true>("dpt4 tile512x2 table1024 swizzled"),
+        make_entry<4, 512, 2, 1024, 3>("dpt4 tile512x2 table1024 3 blocks/SM"),
+        make_entry<2, 512, 2, 1024, 2>("dpt2 tile512x2 table1024"),
+        make_entry<4, 512, 2, 1024, 2>("dpt4 tile512x2 table1024 2 blocks/SM"),
+        make_entry<1, 512, 2, 1024, 2>("dpt1 tile512x2 table1024"),
+        make_entry<4, 512, 2, 512, 2>("dpt4 tile512x2 table512"),
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));
     return entries;
