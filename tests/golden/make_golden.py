@@ -342,6 +342,63 @@ def gen_psf(out):
         out[f"{tag}/I"], out[f"{tag}/x"], out[f"{tag}/y"], out[f"{tag}/E"] = I, x_im, y_im, E
 
 
+def gen_ray_mpmath(out, akb_chain):
+    """The reference's mpmath twins (AKB_raytrace_III_I_20250710.py:275-313, 325-377, 413-467), executed
+    at 30 digits on 48 rays of the AKB chain: a >FP64 truth for the 1e-12 gate, and the per-ray NaN
+    flavour of a miss (III_I:296-301)."""
+    import ast
+    import mpmath
+    from mpmath import mp
+    mp.dps = 30
+    path = os.path.join(R.REF, "AKB_raytrace_III_I_20250710.py")
+    tree = ast.parse(open(path, encoding="utf-8").read(), filename=path)
+    want = {"mirr_ray_intersection", "norm_vector", "normalize_vector", "reflect_ray", "plane_ray_intersection",
+            "mpmath_norm"}
+    defs = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in want]
+    ns = {"np": np}
+    for name in ("mp", "mpf", "sin", "cos", "tan", "sqrt", "pi", "fabs", "asin", "acos", "atan", "isnan", "nan", "matrix", "nstr"):
+        ns[name] = getattr(mpmath, name)
+    exec(compile(ast.Module(body=defs, type_ignores=[]), path, "exec"), ns)
+
+    def to_mp(a):
+        m = mpmath.matrix(a.shape[0], a.shape[1])
+        for i in range(a.shape[0]):
+            for j in range(a.shape[1]):
+                m[i, j] = mpmath.mpf(float(a[i, j]))
+        return m
+
+    def to_np(m):
+        return np.array([[float(m[i, j]) for j in range(m.cols)] for i in range(m.rows)])
+
+    n = akb_chain["tan_h"].shape[0]
+    sel = np.linspace(0, n * n - 1, 48).astype(int)
+    ray = akb_chain["ray0"][:, sel]
+    src = np.repeat(akb_chain["source_point"][:, None], len(sel), axis=1)
+    out["ray"], out["source"] = ray, src
+    out["coeffs"], out["negative"], out["plane"] = akb_chain["coeffs"], akb_chain["negative"], akb_chain["plane"]
+    cur_ray, cur_src = to_mp(ray), to_mp(src)
+    for k in range(4):
+        co = [mpmath.mpf(float(v)) for v in akb_chain["coeffs"][k]]
+        p = ns["mirr_ray_intersection"](co, cur_ray, cur_src, negative=bool(akb_chain["negative"][k]))
+        nv = ns["norm_vector"](co, p)
+        rf = ns["reflect_ray"](cur_ray, nv)
+        out[f"P{k}"], out[f"N{k}"], out[f"R{k}"] = to_np(p), to_np(nv), to_np(rf)
+        cur_ray, cur_src = rf, p
+    det = ns["plane_ray_intersection"]([mpmath.mpf(float(v)) for v in akb_chain["plane"]], cur_ray, cur_src)
+    out["det"] = to_np(det)
+    # per-ray miss: ray 5 starts at the centre of the first (hyperbolic) quadric and runs along z,
+    # between the two branches: D < 0 for this ray only
+    ray_m, src_m = ray.copy(), src.copy()
+    c0 = akb_chain["coeffs"][0]
+    ray_m[:, 5] = [0.0, 0.0, 1.0]
+    src_m[:, 5] = [-c0[6] / (2 * c0[0]), 0.0, 0.0]
+    co0 = [mpmath.mpf(float(v)) for v in akb_chain["coeffs"][0]]
+    pm = ns["mirr_ray_intersection"](co0, to_mp(ray_m), to_mp(src_m))
+    out["miss_ray"], out["miss_source"], out["miss_P0"] = ray_m, src_m, to_np(pm)
+    print("ray mpmath: miss column NaN:", np.isnan(out["miss_P0"][:, 5]).all(), "others finite:",
+          np.isfinite(np.delete(out["miss_P0"], 5, axis=1)).all())
+
+
 def main():
     assert R.available(), "needs /root/reference (build container only)"
     geo = {}
@@ -354,6 +411,8 @@ def main():
     for kind in ("akb", "kb"):
         files[f"chain_{kind}_ref"] = {}
         gen_chain(files[f"chain_{kind}_ref"], geo, kind)
+    files["ray_mp_ref"] = {}
+    gen_ray_mpmath(files["ray_mp_ref"], files["chain_akb_ref"])
     files["geometry"] = geo
     pkg_data = os.path.join(os.path.dirname(os.path.dirname(HERE)), "akbraytracing_b200", "data")
     os.makedirs(pkg_data, exist_ok=True)
