@@ -66,7 +66,10 @@ __device__ __forceinline__ void sqrt_and_half_rinv(double s, double &root, doubl
 {
     double y = rsqrt_approx(s);
     double g = mul(s, y);
-    double h = mul(0.5, y);
+    // y/2 by decrementing the exponent field on the integer pipe (exact; the low word of the MUFU
+    // result is zero): one FP64-pipe slot less per pair.  y = inf / 0 / NaN only arise together
+    // with g = NaN (s = 0, inf, NaN), which poisons every later step exactly as before.
+    double h = __hiloint2double(__double2hiint(y) - 0x00100000, 0);
     double e = fma_(-g, h, 0.5);
     g = fma_(g, e, g);
     h = fma_(h, e, h);

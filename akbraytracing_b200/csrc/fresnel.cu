@@ -27,9 +27,19 @@ namespace {
 
 using namespace akb;
 
-constexpr int ROWS = 5; // sx, sy, sz, w_re, w_im
 constexpr int HEAD = 4; // per-tile header after the rows: reference point c_T (x, y, z) + pad
 constexpr int THREADS = 256;
+
+// Formulation flags of a kernel variant (template parameter FORM).
+//   FORM_TAN      rotate with tan f:  h e^{-i(theta+f)} = cf (C - S tan f) - i cf (S + C tan f),  cf = h cos f
+//   FORM_SHORTCOS cos f = 1 - f^2/2  (only where |f| <= pi/2048: the f^4/24 term is <= 2.3e-13)
+//   FORM_POLAR    sources carry |w|, and arg(w) is folded into the phase: the whole multiples of the
+//                 table step go into the rounding constant (MAGIC - m_j, i.e. into the table index, free),
+//                 the remainder is added to f (one DADD); the complex multiply-accumulate with w_j
+//                 (4 DFMA) becomes a real one (2 DFMA).
+enum { FORM_TAN = 1, FORM_SHORTCOS = 2, FORM_POLAR = 4 };
+// rows of a packed source tile: sx, sy, sz, then (w_re, w_im) or (|w|, -frac(arg w), MAGIC - m)
+__host__ __device__ constexpr int rows_of(int form) { return (form & FORM_POLAR) ? 6 : 5; }
 
 struct PhaseConst {
     double k;        // FAITHFUL: phase = fl(k * r)
@@ -45,8 +55,10 @@ struct PhaseConst {
 __global__ void pack_sources_kernel(const double *__restrict__ sx, const double *__restrict__ sy,
                                     const double *__restrict__ sz, const double *__restrict__ u,
                                     const double *__restrict__ ds, long long N, long long padded, int tile,
-                                    int relative, double *__restrict__ packed)
+                                    int relative, int polar, double inv_u, double neg_u_hi, double neg_u_lo,
+                                    double *__restrict__ packed)
 {
+    const int ROWS = polar ? 6 : 5;
     long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= padded) return;
     long long jj = j < N ? j : N - 1; // padding repeats the last point (finite r) with zero weight
@@ -68,8 +80,20 @@ __global__ void pack_sources_kernel(const double *__restrict__ sx, const double 
     t[0 * tile + o] = relative ? sub(sx[jj], cx) : sx[jj];
     t[1 * tile + o] = relative ? sub(sy[jj], cy) : sy[jj];
     t[2 * tile + o] = relative ? sub(sz[jj], cz) : sz[jj];
-    t[3 * tile + o] = wr;
-    t[4 * tile + o] = wi;
+    if (polar) {
+        // w = |w| e^{i phi},  phi = m u + g  (u = table step, m integer, |g| <= u/2):
+        //   w e^{-i p} = |w| e^{-i((p - g) - m u)}  ->  table index n - m, remainder f - g
+        const double mag = hypot(wr, wi);
+        const double phi = mag > 0.0 ? atan2(wi, wr) : 0.0;
+        const double m = rint(mul(phi, inv_u));
+        const double g = fma_(m, neg_u_lo, fma_(m, neg_u_hi, phi));
+        t[3 * tile + o] = mag;
+        t[4 * tile + o] = -g;
+        t[5 * tile + o] = sub(AKB_RND_MAGIC, m);
+    } else {
+        t[3 * tile + o] = wr;
+        t[4 * tile + o] = wi;
+    }
     if (o == 0) {
         t[ROWS * tile + 0] = cx;
         t[ROWS * tile + 1] = cy;
@@ -115,11 +139,12 @@ __device__ __forceinline__ void tma_bulk_load(uint32_t dst, const void *src, uin
 // FP64 constants live in constant memory so that they reach the DFMA as a c[bank][offset] /
 // uniform-register operand: as literals ptxas re-materialises each of them with two UMOVs per
 // loop iteration (30 extra issue slots per 4 pairs in the first version of this kernel).
-enum { KC_MAGIC, KC_NEG_MAGIC, KC_T1, KC_T2, KC_TC1, KC_COUNT };
+enum { KC_MAGIC, KC_NEG_MAGIC, KC_T1, KC_T2, KC_TC1, KC_TT1, KC_TT2, KC_COUNT };
 __constant__ double KC[KC_COUNT] = {
     AKB_RND_MAGIC, -AKB_RND_MAGIC,
     -1.0 / 6.0, 1.0 / 120.0, // sin f = f (1 + z (T1 + z T2)),  |f| <= pi/512: next term 1e-17 relative
-    1.0 / 24.0};             // cos f = 1 + z (-1/2 + z TC1),              next term 8e-17
+    1.0 / 24.0,              // cos f = 1 + z (-1/2 + z TC1),              next term 8e-17
+    1.0 / 3.0, 2.0 / 15.0};  // tan f = f (1 + z (TT1 + z TT2)),           next term 17/315 z^3
 
 // ---------------------------------------------------------------- one (detector, source) pair, in three phases
 //
@@ -249,54 +274,64 @@ __device__ __forceinline__ PairA pair_phase_a(double X, double Y, double Z, doub
     return a;
 }
 
-// Byte address of table entry (q mod TBL).  The table is aligned to its own size, so the index bits
-// can be OR-ed into the base with one LOP3.  (An XOR swizzle of the bank-group bits that spreads
-// power-of-two index strides across the lanes was measured: its two extra ALU instructions per pair
-// cost more issue slots than the bank conflicts it removes, 442 vs 449 Gterms/s on C3.)
+// Table entry (q mod TBL): one LOP3 for the index, then LDS.128 [R.X16 + UR] -- the scaling and the
+// (uniform) table base ride in the load's address mode, so the table needs no alignment.  (An XOR
+// swizzle of the bank-group bits that spreads power-of-two index strides across the lanes was
+// measured: its two extra ALU instructions per pair cost more issue slots than the bank conflicts
+// it removes, 442 vs 449 Gterms/s on C3.)
 template <int TBL>
-__device__ __forceinline__ uint32_t table_slot(int q, uint32_t table_s)
+__device__ __forceinline__ double2 table_entry(const double2 *table, int q)
 {
-    uint32_t addr;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(addr) : "r"(q << 4), "n"((TBL - 1) << 4), "r"(table_s));
-    return addr;
-}
-
-__device__ __forceinline__ double2 lds_double2(uint32_t addr)
-{
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-    return v;
+    return table[q & (TBL - 1)];
 }
 
 // exact Cody-Waite reduction + h*(cos f, sin f): n = rint(p/u), f = p - n*u.  fma(n, -u_hi, p) is
 // exact (the difference fits in 53 bits); the u_lo term restores the bits of u beyond double.
-template <int MODE, int TBL>
-__device__ __forceinline__ void pair_phase_b(const PairA &a, const PhaseConst &pc, double t2, double phi, double &cf,
-                                             double &sf)
+// TAN = false: returns (cf, sf) = h (cos f, sin f).
+// TAN = true:  returns cf = h cos f and sf = tan f, for the rotation  h e^{-i(theta+f)} =
+//              cf (C - S tan f) - i cf (S + C tan f): one FP64 instruction less per pair.
+//
+// FORM_POLAR: `magic_j` = MAGIC - m_j is the rounding constant a.t was formed with and `g_j` the
+// (negated) remainder of the source's weight phase; |f| then reaches pi/TBL * 2.
+template <int MODE, int TBL, int FORM>
+__device__ __forceinline__ void pair_phase_b(const PairA &a, const PhaseConst &pc, double t2, double phi,
+                                             double magic_j, double g_j, double &cf, double &sf)
 {
-    const double n = add(a.t, KC[KC_NEG_MAGIC]);
+    constexpr bool POLAR = (FORM & FORM_POLAR) != 0;
+    constexpr int STEPS = POLAR ? TBL / 2 : TBL; // |f| <= pi / STEPS
+    const double n = POLAR ? sub(a.t, magic_j) : add(a.t, KC[KC_NEG_MAGIC]);
     double f;
     if (MODE == AKB_PHASE_FAITHFUL) {
         f = fma_(n, pc.neg_u_hi, a.p);
         f = fma_(n, pc.neg_u_lo, f);
-    } else if (MODE == AKB_PHASE_REFERENCED) {
-        f = fma_(a.p, pc.q_hi, -n); // exact: (r - r_ref) q_hi - n fits in 53 bits
-        f = add(f, phi);
-        f = fma_(a.p, pc.q_lo, f);
-        f = mul(f, pc.u);
+        if (POLAR) f = add(f, g_j);
     } else {
-        f = fma_(a.p, pc.q_hi, -n);
+        f = fma_(a.p, pc.q_hi, -n); // exact: the difference fits in 53 bits
+        if (MODE == AKB_PHASE_REFERENCED) f = add(f, phi);
         f = fma_(a.p, pc.q_lo, f);
-        f = mul(f, pc.u);
+        f = POLAR ? fma_(f, pc.u, g_j) : mul(f, pc.u);
     }
     const double z = mul(f, f);
+    static_assert(!(FORM & FORM_SHORTCOS) || STEPS >= 2048, "short cosine needs |f| <= pi/2048");
+    const double c1 = (FORM & FORM_SHORTCOS) ? fma_(z, -0.5, 1.0)                          // f^4/24 <= 2.3e-13
+                                             : fma_(z, fma_(KC[KC_TC1], z, -0.5), 1.0);    // cos f
+    if (FORM & FORM_TAN) {
+        double e1;
+        if (STEPS >= 1024) {
+            e1 = fma_(z, KC[KC_TT1], 1.0); // |f| <= pi/1024: the 2 f^5/15 term is <= 3.6e-14 (1.1e-15 at pi/2048)
+        } else {
+            e1 = fma_(z, fma_(t2, z, KC[KC_TT1]), 1.0); // tan f / f  (t2 = 2/15)
+        }
+        sf = mul(f, e1);
+        cf = mul(a.h, c1);
+        return;
+    }
     double e1;
-    if (TBL >= 1024) {
+    if (STEPS >= 1024) {
         e1 = fma_(z, KC[KC_T1], 1.0); // |f| <= pi/1024: the z^2/120 term is 7e-13 of |f| <= 2e-15 absolute
     } else {
         e1 = fma_(z, fma_(t2, z, KC[KC_T1]), 1.0); // sin f / f
     }
-    const double c1 = fma_(z, fma_(KC[KC_TC1], z, -0.5), 1.0); // cos f
     const double hf = mul(a.h, f);
     sf = mul(hf, e1);
     cf = mul(a.h, c1);
@@ -308,21 +343,27 @@ __device__ __forceinline__ void pair_phase_b(const PairA &a, const PhaseConst &p
 // ---------------------------------------------------------------- pair kernel
 // grid.x: blocks of THREADS*DPT detector points; grid.y: splits of the source tiles.
 // out: [gridDim.y][M] complex partial sums (gridDim.y == 1 -> the result itself).
-template <int TILE, int STAGES, int TBL>
+template <int TILE, int STAGES, int TBL, int FORM>
 struct PairCfg {
-    static constexpr int kTileBytes = (ROWS * TILE + HEAD) * 8; // rows + the tile's reference point
+    static constexpr int kRows = rows_of(FORM);
+    static constexpr int kTileBytes = (kRows * TILE + HEAD) * 8; // rows + the tile's reference point
     static constexpr int kTableBytes = TBL * 16;
-    // tiles | mbarriers | 2 loop constants | table (aligned to its own size: that much slack)
-    static constexpr int kSmemBytes = STAGES * kTileBytes + STAGES * 8 + 16 + 2 * kTableBytes;
+    // tiles | mbarriers (padded to 16 B) | 2 loop constants | table
+    static constexpr int kBarBytes = (STAGES * 8 + 15) & ~15;
+    static constexpr int kTableOffset = STAGES * kTileBytes + kBarBytes + 16;
+    static constexpr int kSmemBytes = kTableOffset + kTableBytes;
 };
 
-template <int DPT, int MODE, int TILE, int STAGES, int TBL, int MINB>
+template <int DPT, int MODE, int TILE, int STAGES, int TBL, int MINB, int FORM>
 __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
     const double *__restrict__ det_x, const double *__restrict__ det_y, const double *__restrict__ det_z,
     long long M, const double *__restrict__ packed, int tiles_total, int tiles_per_split, long long n_padded,
     const __grid_constant__ PhaseConst pc, double *__restrict__ out)
 {
-    using Cfg = PairCfg<TILE, STAGES, TBL>;
+    using Cfg = PairCfg<TILE, STAGES, TBL, FORM>;
+    constexpr int ROWS = Cfg::kRows;
+    constexpr bool POLAR = (FORM & FORM_POLAR) != 0;
+    constexpr bool TAN = (FORM & FORM_TAN) != 0;
     constexpr int TILE_DOUBLES = ROWS * TILE + HEAD;
     constexpr bool REF = MODE == AKB_PHASE_REFERENCED;
     constexpr int NP = 2 * DPT; // pairs per loop iteration: DPT detector points x 2 sources
@@ -330,8 +371,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
     double *tiles = reinterpret_cast<double *>(smem_raw);
     const uint32_t tiles_s = smem_u32(tiles);
     const uint32_t bars_s = tiles_s + STAGES * Cfg::kTileBytes;
-    const uint32_t consts_s = bars_s + STAGES * 8;
-    const uint32_t table_s = (consts_s + 16 + Cfg::kTableBytes - 1) & ~(uint32_t)(Cfg::kTableBytes - 1);
+    const uint32_t consts_s = bars_s + Cfg::kBarBytes;
+    double2 *table = reinterpret_cast<double2 *>(smem_raw + Cfg::kTableOffset);
 
     const int t0 = blockIdx.y * tiles_per_split;
     const int t1 = min(t0 + tiles_per_split, tiles_total);
@@ -352,7 +393,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
     for (int m = threadIdx.x; m < TBL; m += THREADS) {
         double sv, cv;
         sincospi((double)m * (2.0 / TBL), &sv, &cv); // exact argument: accurate to < 1 ulp
-        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(table_slot<TBL>(m, table_s)), "d"(cv), "d"(sv) : "memory");
+        table[m] = make_double2(cv, sv);
     }
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -362,7 +403,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
         // fma(T2, z, T1)); a DFMA takes only one constant/uniform operand, and ptxas would re-create
         // the second one with two IMAD.U32 per use.  Bouncing them through shared memory yields
         // loop-invariant VECTOR registers that cannot be re-materialised.
-        asm volatile("st.shared.f64 [%0], %1;" ::"r"(consts_s), "d"(KC[KC_T2]) : "memory");
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(consts_s), "d"(KC[TAN ? KC_TT2 : KC_T2]) : "memory");
         asm volatile("st.shared.f64 [%0], %1;" ::"r"(consts_s + 8), "d"(KC[KC_MAGIC]) : "memory");
     }
     __syncthreads();
@@ -395,26 +436,31 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
             const double2 vx = *reinterpret_cast<const double2 *>(T + 0 * TILE + j);
             const double2 vy = *reinterpret_cast<const double2 *>(T + 1 * TILE + j);
             const double2 vz = *reinterpret_cast<const double2 *>(T + 2 * TILE + j);
+            // (w_re, w_im) of the two sources -- or, FORM_POLAR: (|w|, -frac(arg w)) and MAGIC - m
             const double2 vr = *reinterpret_cast<const double2 *>(T + 3 * TILE + j);
             const double2 vi = *reinterpret_cast<const double2 *>(T + 4 * TILE + j);
+            double2 vm = make_double2(magic, magic);
+            if (POLAR) vm = *reinterpret_cast<const double2 *>(T + 5 * TILE + j);
             PairA a[NP];
             double2 cs[NP];
             double cf[NP], sf[NP];
 #pragma unroll
             for (int d = 0; d < DPT; ++d) {
                 if (REF) {
-                    a[2 * d] = pair_phase_a_ref(rc[d], vx.x, vy.x, vz.x, pc, magic);
-                    a[2 * d + 1] = pair_phase_a_ref(rc[d], vx.y, vy.y, vz.y, pc, magic);
+                    a[2 * d] = pair_phase_a_ref(rc[d], vx.x, vy.x, vz.x, pc, vm.x);
+                    a[2 * d + 1] = pair_phase_a_ref(rc[d], vx.y, vy.y, vz.y, pc, vm.y);
                 } else {
-                    a[2 * d] = pair_phase_a<MODE>(X[d], Y[d], Z[d], vx.x, vy.x, vz.x, pc, magic);
-                    a[2 * d + 1] = pair_phase_a<MODE>(X[d], Y[d], Z[d], vx.y, vy.y, vz.y, pc, magic);
+                    a[2 * d] = pair_phase_a<MODE>(X[d], Y[d], Z[d], vx.x, vy.x, vz.x, pc, vm.x);
+                    a[2 * d + 1] = pair_phase_a<MODE>(X[d], Y[d], Z[d], vx.y, vy.y, vz.y, pc, vm.y);
                 }
                 const int n_ref = REF ? rc[d].n_ref : 0; // table index = n_ref + rint(k (r - r_ref)/u + phi)
-                cs[2 * d] = lds_double2(table_slot<TBL>(__double2loint(a[2 * d].t) + n_ref, table_s));
-                cs[2 * d + 1] = lds_double2(table_slot<TBL>(__double2loint(a[2 * d + 1].t) + n_ref, table_s));
+                cs[2 * d] = table_entry<TBL>(table, __double2loint(a[2 * d].t) + n_ref);
+                cs[2 * d + 1] = table_entry<TBL>(table, __double2loint(a[2 * d + 1].t) + n_ref);
             }
 #pragma unroll
-            for (int i = 0; i < NP; ++i) pair_phase_b<MODE, TBL>(a[i], pc, t2, REF ? rc[i / 2].phi : 0.0, cf[i], sf[i]);
+            for (int i = 0; i < NP; ++i)
+                pair_phase_b<MODE, TBL, FORM>(a[i], pc, t2, REF ? rc[i / 2].phi : 0.0, (i & 1) ? vm.y : vm.x,
+                                              (i & 1) ? vi.y : vi.x, cf[i], sf[i]);
             // phase C: rotate by the table entry, then accumulate.  The accumulation is ordered by
             // source and by operation so that consecutive DFMAs share their first operand (w_re or
             // w_im of one source): served by the operand-reuse cache, they read 2 registers, not 3.
@@ -423,8 +469,24 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
             for (int i = 0; i < NP; ++i) {
                 const double m1 = mul(cs[i].x, cf[i]);
                 const double m2 = mul(cs[i].y, cf[i]);
-                c[i] = fma_(-cs[i].y, sf[i], m1);
-                sn[i] = fma_(cs[i].x, sf[i], m2);
+                if (TAN) { // sf = tan f
+                    c[i] = fma_(-m2, sf[i], m1);
+                    sn[i] = fma_(m1, sf[i], m2);
+                } else {
+                    c[i] = fma_(-cs[i].y, sf[i], m1);
+                    sn[i] = fma_(cs[i].x, sf[i], m2);
+                }
+            }
+            if (POLAR) { // real weight |w_j|: (c - i sn) |w|
+#pragma unroll
+                for (int d = 0; d < DPT; ++d) ar[d] = fma_(vr.x, c[2 * d], ar[d]);
+#pragma unroll
+                for (int d = 0; d < DPT; ++d) ai[d] = fma_(-vr.x, sn[2 * d], ai[d]);
+#pragma unroll
+                for (int d = 0; d < DPT; ++d) ar[d] = fma_(vr.y, c[2 * d + 1], ar[d]);
+#pragma unroll
+                for (int d = 0; d < DPT; ++d) ai[d] = fma_(-vr.y, sn[2 * d + 1], ai[d]);
+                continue;
             }
 #pragma unroll
             for (int d = 0; d < DPT; ++d) ar[d] = fma_(vr.x, c[2 * d], ar[d]);
@@ -512,12 +574,12 @@ PhaseConst make_phase_const(double k, int table)
 
 struct KernelEntry {
     const char *name;
-    int dpt, tile, stages, table;
+    int dpt, tile, stages, table, form;
     const void *fn[3]; // per mode
     int smem;
 };
 
-template <int DPT, int TILE, int STAGES, int TBL, int MINB>
+template <int DPT, int TILE, int STAGES, int TBL, int MINB, int FORM>
 KernelEntry make_entry(const char *name)
 {
     KernelEntry e;
@@ -526,10 +588,11 @@ KernelEntry make_entry(const char *name)
     e.tile = TILE;
     e.stages = STAGES;
     e.table = TBL;
-    e.fn[0] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_FAITHFUL, TILE, STAGES, TBL, MINB>);
-    e.fn[1] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_EXACT, TILE, STAGES, TBL, MINB>);
-    e.fn[2] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_REFERENCED, TILE, STAGES, TBL, MINB>);
-    e.smem = PairCfg<TILE, STAGES, TBL>::kSmemBytes;
+    e.fn[0] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_FAITHFUL, TILE, STAGES, TBL, MINB, FORM>);
+    e.fn[1] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_EXACT, TILE, STAGES, TBL, MINB, FORM>);
+    e.fn[2] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_REFERENCED, TILE, STAGES, TBL, MINB, FORM>);
+    e.smem = PairCfg<TILE, STAGES, TBL, FORM>::kSmemBytes;
+    e.form = FORM;
     return e;
 }
 
@@ -538,11 +601,15 @@ KernelEntry make_entry(const char *name)
 const KernelEntry *kernel_table(int *count)
 {
     static const KernelEntry entries[] = {
-        make_entry<4, 512, 2, 1024, 3>("dpt4 tile512x2 table1024 3 blocks/SM"),
-        make_entry<2, 512, 2, 1024, 2>("dpt2 tile512x2 table1024"),
-        make_entry<4, 512, 2, 1024, 2>("dpt4 tile512x2 table1024 2 blocks/SM"),
-        make_entry<1, 512, 2, 1024, 2>("dpt1 tile512x2 table1024"),
-        make_entry<4, 512, 2, 512, 2>("dpt4 tile512x2 table512"),
+        make_entry<4, 256, 3, 2048, 3, FORM_TAN | FORM_POLAR>("dpt4 tile256x3 table2048 tan polar 3 blocks/SM"),
+        make_entry<2, 512, 2, 1024, 2, FORM_TAN | FORM_POLAR>("dpt2 tile512x2 table1024 tan polar"),
+        make_entry<4, 512, 2, 1024, 3, 0>("dpt4 tile512x2 table1024 sincos 3 blocks/SM"),
+        make_entry<1, 512, 2, 1024, 2, FORM_TAN | FORM_POLAR>("dpt1 tile512x2 table1024 tan polar"),
+        make_entry<4, 512, 2, 2048, 3, FORM_TAN>("dpt4 tile512x2 table2048 tan 3 blocks/SM"),
+        make_entry<4, 512, 2, 2048, 3, FORM_TAN | FORM_SHORTCOS>("dpt4 tile512x2 table2048 tan shortcos 3 blocks/SM"),
+        make_entry<4, 256, 3, 4096, 2, FORM_TAN | FORM_POLAR | FORM_SHORTCOS>(
+            "dpt4 tile256x3 table4096 tan polar shortcos 2 blocks/SM"),
+        make_entry<4, 512, 2, 2048, 2, FORM_TAN | FORM_POLAR>("dpt4 tile512x2 table2048 tan polar 2 blocks/SM"),
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));
     return entries;
@@ -673,15 +740,16 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     if ((rc = timing_mark(0, st))) return rc;
 
     double *packed = nullptr, *partial = nullptr;
-    AKB_CUDA(cudaMallocAsync(&packed, (size_t)tiles_total * (ROWS * TILE + HEAD) * sizeof(double), st));
+    const int rows = rows_of(ke.form);
+    AKB_CUDA(cudaMallocAsync(&packed, (size_t)tiles_total * (rows * TILE + HEAD) * sizeof(double), st));
     if (splits > 1) AKB_CUDA(cudaMallocAsync(&partial, (size_t)splits * M * 2 * sizeof(double), st));
 
-    pack_sources_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, st>>>(src_x, src_y, src_z, src_u, src_ds, N,
-                                                                          padded, TILE,
-                                                                          mode == AKB_PHASE_REFERENCED ? 1 : 0, packed);
+    PhaseConst pc = make_phase_const(k, ke.table);
+    pack_sources_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, st>>>(
+        src_x, src_y, src_z, src_u, src_ds, N, padded, TILE, mode == AKB_PHASE_REFERENCED ? 1 : 0,
+        (ke.form & FORM_POLAR) ? 1 : 0, pc.inv_u, pc.neg_u_hi, pc.neg_u_lo, packed);
     AKB_LAUNCH_CHECK();
 
-    PhaseConst pc = make_phase_const(k, ke.table);
     double *dst = splits > 1 ? partial : out;
     if ((rc = timing_mark(1, st))) return rc;
     {
