@@ -4,21 +4,24 @@
 //
 // Replaces the ten CuPy elementwise launches + ZGEMV of GPU0402:112-121 (and the numba loop of
 // CPU0402:71-85) with ONE kernel that never materialises the (batch x N_back) matrix:
-//   * a small pack kernel fuses u*ds (CPU0402:102 / K6), pads the source set to whole tiles and
-//     lays it out tile-contiguous [tile][sx|sy|sz|w_re|w_im][TILE] so that one TMA bulk copy
+//   * a small pack kernel fuses u*ds (CPU0402:102 / K6), turns the weight into polar form
+//     (|w|, arg w split into whole table steps + remainder), pads the source set to whole tiles
+//     and lays it out tile-contiguous [tile][sx|sy|sz|a|g|magic][TILE] so that one TMA bulk copy
 //     (cp.async.bulk -> SASS UBLKCP) brings a tile into shared memory;
 //   * the pair kernel keeps DPT detector points + their complex accumulators in registers and
 //     streams source tiles through an mbarrier ring;
-//   * per pair: r = sqrt(dx^2+dy^2+dz^2) from one MUFU.RSQ64H + 7 FP64 ops (correctly rounded,
+//   * per pair: r = sqrt(dx^2+dy^2+dz^2) from one MUFU.RSQ64H + 6 FP64 ops (correctly rounded,
 //     also yields 1/(2r)), the phase k*r reduced EXACTLY (Cody-Waite with FMA) to a multiple of
-//     2*pi/1024 plus a remainder |f| <= pi/1024, exp(-i f) from a short polynomial, and the
-//     multiple looked up in a 1024-entry (cos, sin) table in shared memory: 35 FP64-pipe
-//     instructions and ~6 others per pair, no libdevice sincos (its Payne-Hanek slow path is
-//     unusable at k*r ~ 1e9);
+//     2*pi/4096 plus a remainder, the weight phase folded into the table index and the remainder,
+//     cos/tan of the remainder from two-term polynomials, the multiple looked up in a 4096-entry
+//     (cos, sin) table in shared memory, a real multiply-accumulate: 31 FP64-pipe instructions
+//     and ~8 others per pair, no libdevice sincos (its Payne-Hanek slow path is unusable at
+//     k*r ~ 1e9);
 //   * three phase modes: FAITHFUL (NumPy/numba rounding, the parity default), EXACT (k*r never
 //     rounded), REFERENCED (optical path relative to a per-tile reference point);
-//   * bound: FP64 ALU (DFMA pipe, 64 lanes/SM).  HBM traffic is 40 B per source per
-//     detector block, i.e. ~0 B per pair; there is no dense contraction, so no tensor cores.
+//   * bound: FP64 ALU (DFMA pipe, 64 lanes/SM; the FP64 tensor path shares that pipe,
+//     tools/ubench/fp64_dmma.cu).  HBM traffic is 48 B per source per detector block, i.e. ~0 B
+//     per pair; there is no dense contraction, so no tensor cores.
 #include <stdlib.h>
 
 #include "akb_common.cuh"
@@ -28,7 +31,6 @@ namespace {
 using namespace akb;
 
 constexpr int HEAD = 4; // per-tile header after the rows: reference point c_T (x, y, z) + pad
-constexpr int THREADS = 256;
 
 // Formulation flags of a kernel variant (template parameter FORM).
 //   FORM_TAN      rotate with tan f:  h e^{-i(theta+f)} = cf (C - S tan f) - i cf (S + C tan f),  cf = h cos f
@@ -153,7 +155,7 @@ __constant__ double KC[KC_COUNT] = {
 // 64-bit vector registers that the operand-reuse cache does not supply.  Constants (c[], uniform
 // registers, immediates) are free.  Hence: polynomials are closed with the constant 1.0, the
 // amplitude is applied by plain multiplications, and accumulations are ordered so that consecutive
-// instructions share an operand.  Per pair (FAITHFUL): 36 FP64 instructions, 5 of them 3-read.
+// instructions share an operand.  Per pair (FAITHFUL, default variant): 31 FP64 instructions, ~3 of them 3-read.
 //
 // The 2*DPT pairs of one loop iteration go through the phases together, which puts the table load
 // of a pair ~40 FP64 instructions ahead of its use.
@@ -354,7 +356,7 @@ struct PairCfg {
     static constexpr int kSmemBytes = kTableOffset + kTableBytes;
 };
 
-template <int DPT, int MODE, int TILE, int STAGES, int TBL, int MINB, int FORM>
+template <int DPT, int MODE, int TILE, int STAGES, int TBL, int MINB, int FORM, int SPI, int THREADS>
 __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
     const double *__restrict__ det_x, const double *__restrict__ det_y, const double *__restrict__ det_z,
     long long M, const double *__restrict__ packed, int tiles_total, int tiles_per_split, long long n_padded,
@@ -366,7 +368,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
     constexpr bool TAN = (FORM & FORM_TAN) != 0;
     constexpr int TILE_DOUBLES = ROWS * TILE + HEAD;
     constexpr bool REF = MODE == AKB_PHASE_REFERENCED;
-    constexpr int NP = 2 * DPT; // pairs per loop iteration: DPT detector points x 2 sources
+    static_assert(SPI == 1 || SPI == 2, "1 or 2 sources per loop iteration");
+    constexpr int NP = SPI * DPT; // pairs per loop iteration: DPT detector points x SPI sources
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *tiles = reinterpret_cast<double *>(smem_raw);
     const uint32_t tiles_s = smem_u32(tiles);
@@ -432,38 +435,48 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                 rc[d] = make_ref_ctx(X[d], Y[d], Z[d], T[ROWS * TILE + 0], T[ROWS * TILE + 1], T[ROWS * TILE + 2], pc, magic);
         }
 #pragma unroll 1
-        for (int j = 0; j < cnt; j += 2) {
-            const double2 vx = *reinterpret_cast<const double2 *>(T + 0 * TILE + j);
-            const double2 vy = *reinterpret_cast<const double2 *>(T + 1 * TILE + j);
-            const double2 vz = *reinterpret_cast<const double2 *>(T + 2 * TILE + j);
-            // (w_re, w_im) of the two sources -- or, FORM_POLAR: (|w|, -frac(arg w)) and MAGIC - m
-            const double2 vr = *reinterpret_cast<const double2 *>(T + 3 * TILE + j);
-            const double2 vi = *reinterpret_cast<const double2 *>(T + 4 * TILE + j);
-            double2 vm = make_double2(magic, magic);
-            if (POLAR) vm = *reinterpret_cast<const double2 *>(T + 5 * TILE + j);
+        for (int j = 0; j < cnt; j += SPI) {
+            // rows of the SPI sources of this iteration: x, y, z, then (w_re, w_im) -- or, FORM_POLAR:
+            // (|w|, -frac(arg w), MAGIC - m)
+            double S[6][SPI];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                if (SPI == 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(T + r * TILE + j);
+                    S[r][0] = v.x;
+                    S[r][SPI - 1] = v.y;
+                } else {
+                    S[r][0] = T[r * TILE + j];
+                }
+            }
+            if (!POLAR) {
+#pragma unroll
+                for (int q = 0; q < SPI; ++q) S[5][q] = magic;
+            }
             PairA a[NP];
             double2 cs[NP];
             double cf[NP], sf[NP];
 #pragma unroll
             for (int d = 0; d < DPT; ++d) {
-                if (REF) {
-                    a[2 * d] = pair_phase_a_ref(rc[d], vx.x, vy.x, vz.x, pc, vm.x);
-                    a[2 * d + 1] = pair_phase_a_ref(rc[d], vx.y, vy.y, vz.y, pc, vm.y);
-                } else {
-                    a[2 * d] = pair_phase_a<MODE>(X[d], Y[d], Z[d], vx.x, vy.x, vz.x, pc, vm.x);
-                    a[2 * d + 1] = pair_phase_a<MODE>(X[d], Y[d], Z[d], vx.y, vy.y, vz.y, pc, vm.y);
-                }
                 const int n_ref = REF ? rc[d].n_ref : 0; // table index = n_ref + rint(k (r - r_ref)/u + phi)
-                cs[2 * d] = table_entry<TBL>(table, __double2loint(a[2 * d].t) + n_ref);
-                cs[2 * d + 1] = table_entry<TBL>(table, __double2loint(a[2 * d + 1].t) + n_ref);
+#pragma unroll
+                for (int q = 0; q < SPI; ++q) {
+                    const int i = SPI * d + q;
+                    if (REF) {
+                        a[i] = pair_phase_a_ref(rc[d], S[0][q], S[1][q], S[2][q], pc, S[5][q]);
+                    } else {
+                        a[i] = pair_phase_a<MODE>(X[d], Y[d], Z[d], S[0][q], S[1][q], S[2][q], pc, S[5][q]);
+                    }
+                    cs[i] = table_entry<TBL>(table, __double2loint(a[i].t) + n_ref);
+                }
             }
 #pragma unroll
             for (int i = 0; i < NP; ++i)
-                pair_phase_b<MODE, TBL, FORM>(a[i], pc, t2, REF ? rc[i / 2].phi : 0.0, (i & 1) ? vm.y : vm.x,
-                                              (i & 1) ? vi.y : vi.x, cf[i], sf[i]);
+                pair_phase_b<MODE, TBL, FORM>(a[i], pc, t2, REF ? rc[i / SPI].phi : 0.0, S[5][i % SPI], S[4][i % SPI],
+                                              cf[i], sf[i]);
             // phase C: rotate by the table entry, then accumulate.  The accumulation is ordered by
-            // source and by operation so that consecutive DFMAs share their first operand (w_re or
-            // w_im of one source): served by the operand-reuse cache, they read 2 registers, not 3.
+            // source and by operation so that consecutive DFMAs share their first operand (the weight
+            // of one source): served by the operand-reuse cache, they read 2 registers, not 3.
             double c[NP], sn[NP];
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
@@ -477,33 +490,20 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                     sn[i] = fma_(cs[i].x, sf[i], m2);
                 }
             }
-            if (POLAR) { // real weight |w_j|: (c - i sn) |w|
 #pragma unroll
-                for (int d = 0; d < DPT; ++d) ar[d] = fma_(vr.x, c[2 * d], ar[d]);
+            for (int q = 0; q < SPI; ++q) {
+                const double wr = S[3][q], wi = S[4][q]; // POLAR: wr = |w_j| (real weight), wi unused
 #pragma unroll
-                for (int d = 0; d < DPT; ++d) ai[d] = fma_(-vr.x, sn[2 * d], ai[d]);
+                for (int d = 0; d < DPT; ++d) ar[d] = fma_(wr, c[SPI * d + q], ar[d]);
 #pragma unroll
-                for (int d = 0; d < DPT; ++d) ar[d] = fma_(vr.y, c[2 * d + 1], ar[d]);
+                for (int d = 0; d < DPT; ++d) ai[d] = fma_(-wr, sn[SPI * d + q], ai[d]);
+                if (!POLAR) {
 #pragma unroll
-                for (int d = 0; d < DPT; ++d) ai[d] = fma_(-vr.y, sn[2 * d + 1], ai[d]);
-                continue;
+                    for (int d = 0; d < DPT; ++d) ai[d] = fma_(wi, c[SPI * d + q], ai[d]);
+#pragma unroll
+                    for (int d = 0; d < DPT; ++d) ar[d] = fma_(wi, sn[SPI * d + q], ar[d]);
+                }
             }
-#pragma unroll
-            for (int d = 0; d < DPT; ++d) ar[d] = fma_(vr.x, c[2 * d], ar[d]);
-#pragma unroll
-            for (int d = 0; d < DPT; ++d) ai[d] = fma_(-vr.x, sn[2 * d], ai[d]);
-#pragma unroll
-            for (int d = 0; d < DPT; ++d) ai[d] = fma_(vi.x, c[2 * d], ai[d]);
-#pragma unroll
-            for (int d = 0; d < DPT; ++d) ar[d] = fma_(vi.x, sn[2 * d], ar[d]);
-#pragma unroll
-            for (int d = 0; d < DPT; ++d) ar[d] = fma_(vr.y, c[2 * d + 1], ar[d]);
-#pragma unroll
-            for (int d = 0; d < DPT; ++d) ai[d] = fma_(-vr.y, sn[2 * d + 1], ai[d]);
-#pragma unroll
-            for (int d = 0; d < DPT; ++d) ai[d] = fma_(vi.y, c[2 * d + 1], ai[d]);
-#pragma unroll
-            for (int d = 0; d < DPT; ++d) ar[d] = fma_(vi.y, sn[2 * d + 1], ar[d]);
         }
         __syncthreads(); // every thread is done with this stage
         if (threadIdx.x == 0 && t + STAGES < t1) {
@@ -574,12 +574,12 @@ PhaseConst make_phase_const(double k, int table)
 
 struct KernelEntry {
     const char *name;
-    int dpt, tile, stages, table, form;
+    int dpt, tile, stages, table, form, threads;
     const void *fn[3]; // per mode
     int smem;
 };
 
-template <int DPT, int TILE, int STAGES, int TBL, int MINB, int FORM>
+template <int DPT, int TILE, int STAGES, int TBL, int MINB, int FORM, int SPI = 2, int THREADS = 256>
 KernelEntry make_entry(const char *name)
 {
     KernelEntry e;
@@ -588,27 +588,30 @@ KernelEntry make_entry(const char *name)
     e.tile = TILE;
     e.stages = STAGES;
     e.table = TBL;
-    e.fn[0] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_FAITHFUL, TILE, STAGES, TBL, MINB, FORM>);
-    e.fn[1] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_EXACT, TILE, STAGES, TBL, MINB, FORM>);
-    e.fn[2] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_REFERENCED, TILE, STAGES, TBL, MINB, FORM>);
+    e.fn[0] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_FAITHFUL, TILE, STAGES, TBL, MINB, FORM, SPI, THREADS>);
+    e.fn[1] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_EXACT, TILE, STAGES, TBL, MINB, FORM, SPI, THREADS>);
+    e.fn[2] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_REFERENCED, TILE, STAGES, TBL, MINB, FORM, SPI, THREADS>);
     e.smem = PairCfg<TILE, STAGES, TBL, FORM>::kSmemBytes;
     e.form = FORM;
+    e.threads = THREADS;
     return e;
 }
 
-// Kernel variants: <points per thread, tile, stages, table entries, min resident blocks/SM>.
-// Entries 0, 1, 3 are used by the size-aware default choice; AKB_FRESNEL_VARIANT=<n> forces one.
+// Kernel variants: <points per thread, tile, stages, table entries, min resident blocks/SM, formulation
+// [, sources per iteration, threads]>.  Entries 0, 1, 3 are used by the size-aware default choice;
+// AKB_FRESNEL_VARIANT=<n> forces one (tools/variant_bench.py).
 const KernelEntry *kernel_table(int *count)
 {
     static const KernelEntry entries[] = {
-        make_entry<4, 256, 3, 2048, 3, FORM_TAN | FORM_POLAR>("dpt4 tile256x3 table2048 tan polar 3 blocks/SM"),
-        make_entry<2, 512, 2, 1024, 2, FORM_TAN | FORM_POLAR>("dpt2 tile512x2 table1024 tan polar"),
-        make_entry<4, 512, 2, 1024, 3, 0>("dpt4 tile512x2 table1024 sincos 3 blocks/SM"),
-        make_entry<1, 512, 2, 1024, 2, FORM_TAN | FORM_POLAR>("dpt1 tile512x2 table1024 tan polar"),
-        make_entry<4, 512, 2, 2048, 3, FORM_TAN>("dpt4 tile512x2 table2048 tan 3 blocks/SM"),
-        make_entry<4, 512, 2, 2048, 3, FORM_TAN | FORM_SHORTCOS>("dpt4 tile512x2 table2048 tan shortcos 3 blocks/SM"),
+        // default: 31 FP64 instructions per pair, 122 registers, 2 x 256 threads per SM (measured best:
+        // 3 blocks/SM at 80 registers spill, 1 block/SM starves the FP64 pipe, block sizes that are not a
+        // multiple of 4 warps lose 10-20 %)
         make_entry<4, 256, 3, 4096, 2, FORM_TAN | FORM_POLAR | FORM_SHORTCOS>(
             "dpt4 tile256x3 table4096 tan polar shortcos 2 blocks/SM"),
+        make_entry<2, 512, 2, 1024, 2, FORM_TAN | FORM_POLAR>("dpt2 tile512x2 table1024 tan polar"),
+        // the round-1 formulation (sin/cos polynomials, complex weights), kept for A/B runs
+        make_entry<4, 512, 2, 1024, 3, 0>("dpt4 tile512x2 table1024 sincos 3 blocks/SM"),
+        make_entry<1, 512, 2, 1024, 2, FORM_TAN | FORM_POLAR>("dpt1 tile512x2 table1024 tan polar"),
         make_entry<4, 512, 2, 2048, 2, FORM_TAN | FORM_POLAR>("dpt4 tile512x2 table2048 tan polar 2 blocks/SM"),
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));
@@ -634,7 +637,7 @@ const KernelEntry &selected_kernel(int mode, long long M = -1, long long N = -1,
         const int order[3] = {pick, 1, 3}; // 4 (or 2), 2, 1 points per thread
         for (int o = 0; o < 3; ++o) {
             pick = order[o];
-            const long long blocks = (M + THREADS * e[pick].dpt - 1) / (THREADS * e[pick].dpt);
+            const long long blocks = (M + e[pick].threads * e[pick].dpt - 1) / (e[pick].threads * e[pick].dpt);
             const long long tiles = (N + e[pick].tile - 1) / e[pick].tile;
             if (blocks * tiles >= 2LL * sms || e[pick].dpt == 1) break;
         }
@@ -706,10 +709,10 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     // ---- plan: split the source tiles so the grid fills whole waves
     int per_sm = 1;
     AKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ke.smem));
-    AKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, ke.smem));
+    AKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ke.threads, ke.smem));
     if (per_sm < 1) per_sm = 1;
     const long long slots = (long long)sms * per_sm;
-    const long long blocks_x = (M + THREADS * ke.dpt - 1) / (THREADS * ke.dpt);
+    const long long blocks_x = (M + ke.threads * ke.dpt - 1) / (ke.threads * ke.dpt);
     int splits = 1;
     {
         double best = -1.0;
@@ -759,7 +762,7 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
         void *args[] = {(void *)&det_x, (void *)&det_y, (void *)&det_z, (void *)&M_, (void *)&pk, (void *)&tt,
                         (void *)&tiles_per_split, (void *)&n_padded, (void *)&pc, (void *)&dst};
         dim3 grid((unsigned)blocks_x, (unsigned)splits);
-        AKB_CUDA(cudaLaunchKernel(kern, grid, dim3(THREADS), args, (size_t)ke.smem, st));
+        AKB_CUDA(cudaLaunchKernel(kern, grid, dim3(ke.threads), args, (size_t)ke.smem, st));
         count_launch();
     }
     if ((rc = timing_mark(2, st))) return rc;

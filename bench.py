@@ -38,8 +38,8 @@ GRID = 512            # focal grid side per rank
 RAYS = 1000           # ray grid side -> 1e6 source points
 WAVELENGTH = 13.5e-9  # CPU0402:243
 ALG_FLOP_PER_TERM = 23.0   # SURVEY.md 8(d) convention
-EXEC_FLOP_PER_TERM = 52.0  # 17 DFMA (x2) + 12 DMUL + 6 DADD issued per pair (faithful mode, counted in the SASS loop)
-FP64_INSTR_PER_TERM = 35.0  # each occupies the FP64 pipe of an SM sub-partition for >= 2 cycles
+EXEC_FLOP_PER_TERM = 45.0  # 14 DFMA (x2) + 10 DMUL + 7 DADD issued per pair (faithful mode, counted in the SASS loop)
+FP64_INSTR_PER_TERM = 31.0  # each occupies the FP64 pipe of an SM sub-partition for >= 2 cycles
 
 
 def measured_peaks():
@@ -320,9 +320,9 @@ def run_ours(args):
             "kernel": "fresnel_pairs_kernel<faithful> [%s]" % L.akb_fresnel_variant_name().decode(), "bound": "fp64",
             "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of THIS launch (1e6 sources x 512x512 detectors,
-            # 8 source splits) from ncu --set full: profiles/r01_ncu_full_bench_launch.md (48.1 MB + 8.9 MB).
-            # Algorithmic bytes: 40 MB packed sources + 6.3 MB detector xyz + 33.5 MB partial sums.
-            "traffic": 57.0e6 if world == 1 else None, "traffic_unit": "bytes per launch (ncu, round 1)",
+            # 8 source splits) from ncu --set full: profiles/r01b_ncu_full_bench_launch.md (57.2 MB + 13.5 MB).
+            # Algorithmic bytes: 48 MB packed sources + 6.3 MB detector xyz + 33.5 MB partial sums (L2-resident).
+            "traffic": 70.7e6 if world == 1 else None, "traffic_unit": "bytes per launch (ncu, round 1)",
             "peak_source": "on-box DFMA microbenchmark (akb_fp64_peak_probe, measured in this run); "
                            "MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
             "algorithmic_flop_per_term": ALG_FLOP_PER_TERM,
@@ -336,6 +336,19 @@ def run_ours(args):
             "kernel_ms": pair_mean, "kernel_share_of_step": pair_mean * args.steps / total_ms,
             "terms_per_s_kernel": pair_terms / (pair_mean * 1e-3), "plan": plan,
         }
+        # the reference's GPU path (CuPy, restated in torch) on the first detector points of this rank
+        g_out, g_rate, g_ms = gpu0402_restatement(torch, (dx, dy, dz), (last[0].contiguous(), last[1].contiguous(),
+                                                  last[2].contiguous()), u, ds, k)
+        g_ref = (out[sl] if world > 1 else out)[:g_out.shape[0]]
+        gpu_baseline = {"value": g_rate, "unit": "terms/s", "n_gpus": 1,
+                        "kind": "restatement of forward_propagation_cupy_batch (GPU0402:64-136) in torch on the same "
+                                "B200; cupy is not installed",
+                        "sample": f"{g_out.shape[0]} detector points x {last.shape[1]} sources in batches of 128 "
+                                  f"({g_ms:.1f} ms)",
+                        "rel_l2_vs_fused_kernel": float(torch.linalg.vector_norm(g_out - g_ref) /
+                                                        torch.linalg.vector_norm(g_ref))}
+        del g_out
+        torch.cuda.empty_cache()
         # secondary line: the HBM-bound ray kernel at config C2 (1e7 rays, one mirror)
         ray_roof = bench_ray_c2(akb, workloads, torch, dev, peaks, peak_src)
         result = {
@@ -348,6 +361,7 @@ def run_ours(args):
                     "timer": "host wall clock around the synchronous call, max over ranks",
                     "steps": e2e_steps, "max_abs_diff_vs_device_path": same},
             "gpu_launches": int(launches) * world, "roofline": roofline, "roofline_ray": ray_roof,
+            "gpu_baseline": gpu_baseline,
         }
     if world > 1:
         dist.barrier()
@@ -357,6 +371,38 @@ def run_ours(args):
         print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
+
+
+def gpu0402_restatement(torch, det, src, u, ds, k, batch=128, batches=4):
+    """The reference's CuPy path (GPU0402:64-136: materialised (batch x N_back) temporaries of
+    dist, amplitude, phase, exp, then a ZGEMV), restated op for op in torch because cupy is not
+    installed.  A BASELINE timed next to the fused kernel, never part of the product path.  The
+    reference sizes its batch from free memory / 4 (GPU0402:93-97); here the batch is bounded to
+    2 GiB complex128 temporaries so the sample stays small -- per-term cost does not depend on it."""
+    dx, dy, dz = det
+    sx, sy, sz = src
+    w = u * ds                                                     # GPU0402:67
+    out = torch.empty(batch * batches, dtype=torch.complex128, device=dx.device)
+
+    def one(i):
+        xs, ys, zs = dx[i:i + batch], dy[i:i + batch], dz[i:i + batch]
+        dist = torch.sqrt((xs[:, None] - sx[None, :]) ** 2 + (ys[:, None] - sy[None, :]) ** 2 +
+                          (zs[:, None] - sz[None, :]) ** 2)       # GPU0402:112-116
+        amplitude = 1.0 / dist
+        phase = -k * dist
+        factor = amplitude * torch.exp(1j * phase)
+        out[i:i + batch] = torch.mv(factor, w)                     # cp.dot(u_back_u, factor.T)
+
+    one(0)  # warm-up (allocator, kernels)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for b in range(batches):
+        one(b * batch)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return out, batch * batches * sx.shape[0] / (ms * 1e-3), ms
 
 
 def bench_ray_c2(akb, workloads, torch, dev, peaks, peak_src, n=3163, reps=5):
