@@ -279,8 +279,8 @@ __device__ __forceinline__ PairA pair_phase_a(double X, double Y, double Z, doub
 // Table entry (q mod TBL): one LOP3 for the index, then LDS.128 [R.X16 + UR] -- the scaling and the
 // (uniform) table base ride in the load's address mode, so the table needs no alignment.  (An XOR
 // swizzle of the bank-group bits that spreads power-of-two index strides across the lanes was
-// measured: its two extra ALU instructions per pair cost more issue slots than the bank conflicts
-// it removes, 442 vs 449 Gterms/s on C3.)
+// measured twice: 442 vs 449 Gterms/s on C3 in the round-1 kernel, 522.8 vs 521.7 in the present one --
+// the shared-memory pipe is not what limits this kernel.)
 template <int TBL>
 __device__ __forceinline__ double2 table_entry(const double2 *table, int q)
 {

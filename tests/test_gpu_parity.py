@@ -149,6 +149,39 @@ def test_fresnel_ragged_sizes_against_oracle(akb, M, N):
     assert rel_l2(got_no_ds, oracle.fresnel_sum(x, y, z, sx, sy, sz, u, k, None)) <= 1e-12
 
 
+@pytest.mark.parametrize("M,N", [(64, 2048), (4096, 10000), (40000, 3000)])  # 1, 2 and 4 points per thread
+def test_fresnel_weight_phases_and_magnitudes(akb, M, N):
+    """The pair kernel carries the source weights u*ds in polar form (|w|, arg w folded into the phase
+    table index).  Weights on the axes (arg = 0, +-pi/2, pi, -0.0 parts), zero weights, magnitudes from
+    1e-300 to 1e+200 and phases on a table-step boundary must reproduce the reference's complex product."""
+    rng = np.random.default_rng(N)
+    x = 0.15 + rng.uniform(-1e-4, 1e-4, M); y = rng.uniform(-1e-4, 1e-4, M); z = rng.uniform(-1e-4, 1e-4, M)
+    sx = rng.uniform(-1e-2, 1e-2, N); sy = rng.uniform(-1e-3, 1e-3, N); sz = rng.uniform(-1e-3, 1e-3, N)
+    k = 2 * np.pi / 13.5e-9
+    special = np.array([1, -1, 1j, -1j, 0, -0.0, complex(-1.0, -0.0), complex(0.0, -1e-300), 1e-300 + 1e-300j,
+                        np.exp(1j * np.pi * 3 / 4096), np.exp(-1j * np.pi * 4095 / 4096), np.exp(1j * np.pi / 4096)])
+    u = np.exp(2j * np.pi * rng.uniform(size=N))
+    u[:special.size] = special
+    u[special.size:2 * special.size] = special[::-1] * 3.0
+    ds = rng.uniform(1e-9, 2e-9, N)
+    ref = oracle.fresnel_sum(x, y, z, sx, sy, sz, u, k, ds)
+    for mode in (akb.PHASE_FAITHFUL, akb.PHASE_EXACT, akb.PHASE_REFERENCED):
+        got = akb.fresnel_sum(x, y, z, sx, sy, sz, u, k, ds, mode=mode)
+        err = rel_l2(got, ref)
+        print(f"M={M} N={N} mode {mode}: rel-L2 {err:.2e}")
+        assert err <= (1e-12 if mode == akb.PHASE_FAITHFUL else FIELD_TOL / 10)
+    # magnitudes far from 1 (no overflow in |w|, no loss in the phase)
+    for scale in (1e-290, 1e200):
+        got = akb.fresnel_sum(x, y, z, sx, sy, sz, u * scale, k, None)
+        want = oracle.fresnel_sum(x, y, z, sx, sy, sz, u * scale, k, None)
+        assert rel_l2(got / scale, want / scale) <= 1e-12  # (the norm of the unscaled fields under/overflows)
+    # a non-finite weight poisons every detector point (the reference: inf/nan in every sum), finite ones do not
+    ub = u.copy(); ub[5] = complex(np.inf, 1.0)
+    bad = akb.fresnel_sum(x, y, z, sx, sy, sz, ub, k, ds)
+    assert not np.isfinite(bad).any()
+    assert not np.isfinite(oracle.fresnel_sum(x[:4], y[:4], z[:4], sx, sy, sz, ub, k, ds)).any()
+
+
 def test_fresnel_empty_inputs(akb):
     e = np.zeros(0)
     x = np.array([0.1, 0.2])
