@@ -24,6 +24,8 @@
 //     per pair; there is no dense contraction, so no tensor cores.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "akb_common.cuh"
 
 namespace {
@@ -254,26 +256,45 @@ __device__ __forceinline__ PairA pair_phase_a_ref(const RefCtx &rc, double ex, d
     return a;
 }
 
+// r^2 -> (phase, 1/(2r), MAGIC + rint(phase/u))
+template <int MODE>
+__device__ __forceinline__ PairA pair_phase_a_from_s(double s, const PhaseConst &pc, double magic)
+{
+    PairA a;
+    double root;
+    sqrt_and_half_rinv(s, root, a.h);
+    if (MODE == AKB_PHASE_FAITHFUL) {
+        a.p = mul(pc.k, root); // CPU0402:82: |phase| = fl(k*dist)
+        a.t = fma_(a.p, pc.inv_u, magic);
+    } else {
+        a.p = root;
+        a.t = fma_(root, pc.q_hi, magic); // k*r is never rounded
+    }
+    return a;
+}
+
 template <int MODE>
 __device__ __forceinline__ PairA pair_phase_a(double X, double Y, double Z, double sx, double sy, double sz,
                                               const PhaseConst &pc, double magic)
 {
     const double ddx = sub(X, sx), ddy = sub(Y, sy), ddz = sub(Z, sz);
-    PairA a;
-    double root;
-    if (MODE == AKB_PHASE_FAITHFUL) {
-        // CPU0402:76-80: (dx*dx + dy*dy) + dz*dz, one rounding per operation
-        const double s = add(add(mul(ddx, ddx), mul(ddy, ddy)), mul(ddz, ddz));
-        sqrt_and_half_rinv(s, root, a.h);
-        a.p = mul(pc.k, root); // CPU0402:82: |phase| = fl(k*dist)
-        a.t = fma_(a.p, pc.inv_u, magic);
-    } else {
-        const double s = fma_(ddz, ddz, fma_(ddy, ddy, mul(ddx, ddx)));
-        sqrt_and_half_rinv(s, root, a.h);
-        a.p = root;
-        a.t = fma_(root, pc.q_hi, magic); // k*r is never rounded
-    }
-    return a;
+    // FAITHFUL: CPU0402:76-80, (dx*dx + dy*dy) + dz*dz with one rounding per operation
+    const double s = MODE == AKB_PHASE_FAITHFUL ? add(add(mul(ddx, ddx), mul(ddy, ddy)), mul(ddz, ddz))
+                                                : fma_(ddz, ddz, fma_(ddy, ddy, mul(ddx, ddx)));
+    return pair_phase_a_from_s<MODE>(s, pc, magic);
+}
+
+// The same pair in a "planar row" block (see the kernel): dxx = fl((X - sx)^2) comes from the tile (one
+// value per source for the whole block), ddz = Z - sz is shared by the thread's points.  Same operations
+// in the same order as pair_phase_a, hence the same bits.
+template <int MODE>
+__device__ __forceinline__ PairA pair_phase_a_row(double dxx, double Y, double sy, double ddz, double dzz,
+                                                  const PhaseConst &pc, double magic)
+{
+    const double ddy = sub(Y, sy);
+    const double s = MODE == AKB_PHASE_FAITHFUL ? add(add(dxx, mul(ddy, ddy)), dzz)
+                                                : fma_(ddz, ddz, fma_(ddy, ddy, dxx));
+    return pair_phase_a_from_s<MODE>(s, pc, magic);
 }
 
 // Table entry (q mod TBL): one LOP3 for the index, then LDS.128 [R.X16 + UR] -- the scaling and the
@@ -379,18 +400,34 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
 
     const int t0 = blockIdx.y * tiles_per_split;
     const int t1 = min(t0 + tiles_per_split, tiles_total);
-    const long long base = (long long)blockIdx.x * (THREADS * DPT) + threadIdx.x;
+    // a thread owns DPT CONSECUTIVE detector points: in a meshgrid-ordered focal grid they lie in one row
+    const long long base = ((long long)blockIdx.x * THREADS + threadIdx.x) * DPT;
 
     double X[DPT], Y[DPT], Z[DPT], ar[DPT], ai[DPT];
 #pragma unroll
     for (int d = 0; d < DPT; ++d) {
-        long long i = base + (long long)d * THREADS;
+        long long i = base + d;
         long long ic = i < M ? i : M - 1;
         X[d] = det_x[ic];
         Y[d] = det_y[ic];
         Z[d] = det_z[ic];
         ar[d] = 0.0;
         ai[d] = 0.0;
+    }
+    // "Planar row" block: every detector point of the block has the same x (a detector plane x = const) and
+    // the points of each thread share z (a row of the grid).  Then (X - sx)^2 is one value per SOURCE -- the
+    // block computes it once per tile, in place of the sx row -- and (Z - sz)^2 one value per (thread,
+    // source): 4.5 instead of 8 FP64 instructions for r^2 per pair, bit-identical results.  Detected here
+    // from the coordinates themselves (block-uniform vote), so irregular detector sets (mirror surfaces)
+    // simply take the general loop.
+    bool row = false;
+    if (!REF) {
+        const long long i0 = (long long)blockIdx.x * THREADS * DPT;
+        const double x0 = det_x[i0 < M ? i0 : M - 1];
+        bool mine = true;
+#pragma unroll
+        for (int d = 0; d < DPT; ++d) mine = mine && X[d] == x0 && Z[d] == Z[0];
+        row = __syncthreads_and(mine);
     }
 
     for (int m = threadIdx.x; m < TBL; m += THREADS) {
@@ -421,106 +458,134 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
         }
     }
 
-    int stage = 0;
-    uint32_t parity = 0;
-    for (int t = t0; t < t1; ++t) {
-        mbar_wait(bars_s + 8 * stage, parity);
-        const double *T = tiles + stage * TILE_DOUBLES;
-        const long long left = n_padded - (long long)t * TILE;
-        const int cnt = left < TILE ? (int)left : TILE; // multiple of 2
-        RefCtx rc[REF ? DPT : 1];
-        if (REF) { // once per (detector point, tile): double-double distance to the tile's reference point
+    // one pass over this block's source tiles; ROW selects the planar-row form of r^2
+    auto run_tiles = [&](auto row_tag) {
+        constexpr bool ROW = decltype(row_tag)::value;
+        int stage = 0;
+        uint32_t parity = 0;
+        for (int t = t0; t < t1; ++t) {
+            mbar_wait(bars_s + 8 * stage, parity);
+            double *T = tiles + stage * TILE_DOUBLES;
+            const long long left = n_padded - (long long)t * TILE;
+            const int cnt = left < TILE ? (int)left : TILE; // multiple of 2
+            RefCtx rc[REF ? DPT : 1];
+            if (REF) { // once per (detector point, tile): double-double distance to the tile's reference point
 #pragma unroll
-            for (int d = 0; d < DPT; ++d)
-                rc[d] = make_ref_ctx(X[d], Y[d], Z[d], T[ROWS * TILE + 0], T[ROWS * TILE + 1], T[ROWS * TILE + 2], pc, magic);
-        }
+                for (int d = 0; d < DPT; ++d)
+                    rc[d] = make_ref_ctx(X[d], Y[d], Z[d], T[ROWS * TILE + 0], T[ROWS * TILE + 1], T[ROWS * TILE + 2], pc,
+                                         magic);
+            }
+            if (ROW) { // the sx row becomes fl((x0 - sx)^2), CPU0402:76-77
+                for (int q = threadIdx.x; q < TILE; q += THREADS) {
+                    const double ddx = sub(X[0], T[q]);
+                    T[q] = mul(ddx, ddx);
+                }
+                // generic-proxy writes to a stage that a later bulk copy (async proxy) overwrites
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+            }
 #pragma unroll 1
-        for (int j = 0; j < cnt; j += SPI) {
-            // rows of the SPI sources of this iteration: x, y, z, then (w_re, w_im) -- or, FORM_POLAR:
-            // (|w|, -frac(arg w), MAGIC - m)
-            double S[6][SPI];
+            for (int j = 0; j < cnt; j += SPI) {
+                // rows of the SPI sources of this iteration: x (ROW: dx^2), y, z, then (w_re, w_im) -- or,
+                // FORM_POLAR: (|w|, -frac(arg w), MAGIC - m)
+                double S[6][SPI];
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
-                if (SPI == 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(T + r * TILE + j);
-                    S[r][0] = v.x;
-                    S[r][SPI - 1] = v.y;
-                } else {
-                    S[r][0] = T[r * TILE + j];
-                }
-            }
-            if (!POLAR) {
-#pragma unroll
-                for (int q = 0; q < SPI; ++q) S[5][q] = magic;
-            }
-            PairA a[NP];
-            double2 cs[NP];
-            double cf[NP], sf[NP];
-#pragma unroll
-            for (int d = 0; d < DPT; ++d) {
-                const int n_ref = REF ? rc[d].n_ref : 0; // table index = n_ref + rint(k (r - r_ref)/u + phi)
-#pragma unroll
-                for (int q = 0; q < SPI; ++q) {
-                    const int i = SPI * d + q;
-                    if (REF) {
-                        a[i] = pair_phase_a_ref(rc[d], S[0][q], S[1][q], S[2][q], pc, S[5][q]);
+                for (int r = 0; r < ROWS; ++r) {
+                    if (SPI == 2) {
+                        const double2 v = *reinterpret_cast<const double2 *>(T + r * TILE + j);
+                        S[r][0] = v.x;
+                        S[r][SPI - 1] = v.y;
                     } else {
-                        a[i] = pair_phase_a<MODE>(X[d], Y[d], Z[d], S[0][q], S[1][q], S[2][q], pc, S[5][q]);
+                        S[r][0] = T[r * TILE + j];
                     }
-                    cs[i] = table_entry<TBL>(table, __double2loint(a[i].t) + n_ref);
                 }
-            }
-#pragma unroll
-            for (int i = 0; i < NP; ++i)
-                pair_phase_b<MODE, TBL, FORM>(a[i], pc, t2, REF ? rc[i / SPI].phi : 0.0, S[5][i % SPI], S[4][i % SPI],
-                                              cf[i], sf[i]);
-            // phase C: rotate by the table entry, then accumulate.  The accumulation is ordered by
-            // source and by operation so that consecutive DFMAs share their first operand (the weight
-            // of one source): served by the operand-reuse cache, they read 2 registers, not 3.
-            double c[NP], sn[NP];
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                const double m1 = mul(cs[i].x, cf[i]);
-                const double m2 = mul(cs[i].y, cf[i]);
-                if (TAN) { // sf = tan f
-                    c[i] = fma_(-m2, sf[i], m1);
-                    sn[i] = fma_(m1, sf[i], m2);
-                } else {
-                    c[i] = fma_(-cs[i].y, sf[i], m1);
-                    sn[i] = fma_(cs[i].x, sf[i], m2);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < SPI; ++q) {
-                const double wr = S[3][q], wi = S[4][q]; // POLAR: wr = |w_j| (real weight), wi unused
-#pragma unroll
-                for (int d = 0; d < DPT; ++d) ar[d] = fma_(wr, c[SPI * d + q], ar[d]);
-#pragma unroll
-                for (int d = 0; d < DPT; ++d) ai[d] = fma_(-wr, sn[SPI * d + q], ai[d]);
                 if (!POLAR) {
 #pragma unroll
-                    for (int d = 0; d < DPT; ++d) ai[d] = fma_(wi, c[SPI * d + q], ai[d]);
+                    for (int q = 0; q < SPI; ++q) S[5][q] = magic;
+                }
+                double ddz[SPI], dzz[SPI];
+                if (ROW) {
 #pragma unroll
-                    for (int d = 0; d < DPT; ++d) ar[d] = fma_(wi, sn[SPI * d + q], ar[d]);
+                    for (int q = 0; q < SPI; ++q) {
+                        ddz[q] = sub(Z[0], S[2][q]);
+                        dzz[q] = mul(ddz[q], ddz[q]);
+                    }
+                }
+                PairA a[NP];
+                double2 cs[NP];
+                double cf[NP], sf[NP];
+#pragma unroll
+                for (int d = 0; d < DPT; ++d) {
+                    const int n_ref = REF ? rc[d].n_ref : 0; // table index = n_ref + rint(k (r - r_ref)/u + phi)
+#pragma unroll
+                    for (int q = 0; q < SPI; ++q) {
+                        const int i = SPI * d + q;
+                        if (REF) {
+                            a[i] = pair_phase_a_ref(rc[d], S[0][q], S[1][q], S[2][q], pc, S[5][q]);
+                        } else if (ROW) {
+                            a[i] = pair_phase_a_row<MODE>(S[0][q], Y[d], S[1][q], ddz[q], dzz[q], pc, S[5][q]);
+                        } else {
+                            a[i] = pair_phase_a<MODE>(X[d], Y[d], Z[d], S[0][q], S[1][q], S[2][q], pc, S[5][q]);
+                        }
+                        cs[i] = table_entry<TBL>(table, __double2loint(a[i].t) + n_ref);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NP; ++i)
+                    pair_phase_b<MODE, TBL, FORM>(a[i], pc, t2, REF ? rc[i / SPI].phi : 0.0, S[5][i % SPI],
+                                                  S[4][i % SPI], cf[i], sf[i]);
+                // phase C: rotate by the table entry, then accumulate.  The accumulation is ordered by
+                // source and by operation so that consecutive DFMAs share their first operand (the weight
+                // of one source): served by the operand-reuse cache, they read 2 registers, not 3.
+                double c[NP], sn[NP];
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    const double m1 = mul(cs[i].x, cf[i]);
+                    const double m2 = mul(cs[i].y, cf[i]);
+                    if (TAN) { // sf = tan f
+                        c[i] = fma_(-m2, sf[i], m1);
+                        sn[i] = fma_(m1, sf[i], m2);
+                    } else {
+                        c[i] = fma_(-cs[i].y, sf[i], m1);
+                        sn[i] = fma_(cs[i].x, sf[i], m2);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < SPI; ++q) {
+                    const double wr = S[3][q], wi = S[4][q]; // POLAR: wr = |w_j| (real weight), wi unused
+#pragma unroll
+                    for (int d = 0; d < DPT; ++d) ar[d] = fma_(wr, c[SPI * d + q], ar[d]);
+#pragma unroll
+                    for (int d = 0; d < DPT; ++d) ai[d] = fma_(-wr, sn[SPI * d + q], ai[d]);
+                    if (!POLAR) {
+#pragma unroll
+                        for (int d = 0; d < DPT; ++d) ai[d] = fma_(wi, c[SPI * d + q], ai[d]);
+#pragma unroll
+                        for (int d = 0; d < DPT; ++d) ar[d] = fma_(wi, sn[SPI * d + q], ar[d]);
+                    }
                 }
             }
+            __syncthreads(); // every thread is done with this stage
+            if (threadIdx.x == 0 && t + STAGES < t1) {
+                mbar_expect_tx(bars_s + 8 * stage, Cfg::kTileBytes);
+                tma_bulk_load(tiles_s + stage * Cfg::kTileBytes, packed + (long long)(t + STAGES) * TILE_DOUBLES,
+                              Cfg::kTileBytes, bars_s + 8 * stage);
+            }
+            if (++stage == STAGES) {
+                stage = 0;
+                parity ^= 1;
+            }
         }
-        __syncthreads(); // every thread is done with this stage
-        if (threadIdx.x == 0 && t + STAGES < t1) {
-            mbar_expect_tx(bars_s + 8 * stage, Cfg::kTileBytes);
-            tma_bulk_load(tiles_s + stage * Cfg::kTileBytes, packed + (long long)(t + STAGES) * TILE_DOUBLES,
-                          Cfg::kTileBytes, bars_s + 8 * stage);
-        }
-        if (++stage == STAGES) {
-            stage = 0;
-            parity ^= 1;
-        }
-    }
+    };
+    if (row)
+        run_tiles(std::true_type{});
+    else
+        run_tiles(std::false_type{});
 
     double2 *o = reinterpret_cast<double2 *>(out) + (long long)blockIdx.y * M;
 #pragma unroll
     for (int d = 0; d < DPT; ++d) {
-        long long i = base + (long long)d * THREADS;
+        long long i = base + d;
         if (i < M) o[i] = make_double2(ar[d], ai[d]);
     }
 }

@@ -18,39 +18,43 @@ for b in re.split(r"\n\s*Function : ", txt):
         m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);", line)
         if m:
             ins.append((int(m.group(1), 16), m.group(2).strip()))
-    best = None
+    loops = []
     for addr, text in ins:
         m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d,\s*)?0x([0-9a-f]+)", text)
         if m and int(m.group(1), 16) < addr:
             tgt = int(m.group(1), 16)
             body = [t for a, t in ins if tgt <= a <= addr]
             nd = sum(1 for t in body if re.match(r"D(FMA|MUL|ADD)", t))
-            if best is None or nd > best[0]:
-                best = (nd, body)
-    nd, body = best
-    cyc = 0
-    three = 0
-    prev_reuse = {}  # slot -> register kept by the previous FP64 instruction of this warp
-    other = 0
-    for t in body:
-        m = re.match(r"(DFMA|DMUL|DADD)\s+(R\d+),\s*(.*)", t)
-        if not m:
-            other += 1
-            continue
-        ops = [o.strip() for o in m.group(3).split(",")]
-        regs = []
-        keep = {}
-        for slot, o in enumerate(ops):
-            r = re.match(r"[-|]*\|?(R\d+)(\.reuse)?", o)
-            if r and not o.lstrip("-|").startswith("RZ"):
-                reg = r.group(1)
-                if prev_reuse.get(slot) != reg:
-                    regs.append(reg)
-                if r.group(2):
-                    keep[slot] = reg
-        prev_reuse = keep
-        d = len(set(regs))
-        three += d >= 3
-        cyc += max(2, d)
-    print(f"{name[:100]}\n  FP64 instrs {nd}, 3-read instrs {three}, FP64 pipe cycles {cyc} ({cyc / pairs:.1f}/pair), "
-          f"other instrs {other} ({other / pairs:.1f}/pair)")
+            inner = not any(tgt <= a2 < addr and re.search(r"BRA", t2) and
+                            (lambda mm: mm and int(mm.group(1), 16) < a2 and int(mm.group(1), 16) >= tgt)(
+                                re.search(r"0x([0-9a-f]+)", t2)) for a2, t2 in ins)
+            if nd >= 50 and inner:
+                loops.append((tgt, nd, body))
+    print(name[:100])
+    for tgt, nd, body in loops:
+        cyc = 0
+        three = 0
+        prev_reuse = {}  # slot -> register kept by the previous FP64 instruction of this warp
+        other = 0
+        for t in body:
+            m = re.match(r"(DFMA|DMUL|DADD)\s+(R\d+),\s*(.*)", t)
+            if not m:
+                other += 1
+                continue
+            ops = [o.strip() for o in m.group(3).split(",")]
+            regs = []
+            keep = {}
+            for slot, o in enumerate(ops):
+                r = re.match(r"[-|]*\|?(R\d+)(\.reuse)?", o)
+                if r and not o.lstrip("-|").startswith("RZ"):
+                    reg = r.group(1)
+                    if prev_reuse.get(slot) != reg:
+                        regs.append(reg)
+                    if r.group(2):
+                        keep[slot] = reg
+            prev_reuse = keep
+            d = len(set(regs))
+            three += d >= 3
+            cyc += max(2, d)
+        print(f"  loop at 0x{tgt:x}: FP64 instrs {nd} ({nd / pairs:.2f}/pair), 3-read instrs {three}, FP64 pipe cycles {cyc} "
+              f"({cyc / pairs:.1f}/pair), other instrs {other} ({other / pairs:.1f}/pair)")
