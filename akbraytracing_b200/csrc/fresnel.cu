@@ -670,7 +670,7 @@ const KernelEntry *kernel_table(int *count)
     static const KernelEntry entries[] = {
         // default: 31 FP64 instructions per pair, 122 registers, 2 x 256 threads per SM (measured best:
         // 3 blocks/SM at 80 registers spill, 1 block/SM starves the FP64 pipe, block sizes that are not a
-        // multiple of 4 warps lose 10-20 %)
+        // multiple of 4 warps lose 10-20 %, one 640/768-thread block per SM sharing one table loses 2-4 %)
         make_entry<4, 256, 3, 4096, 2, FORM_TAN | FORM_POLAR | FORM_SHORTCOS>(
             "dpt4 tile256x3 table4096 tan polar shortcos 2 blocks/SM"),
         make_entry<2, 512, 2, 1024, 2, FORM_TAN | FORM_POLAR>("dpt2 tile512x2 table1024 tan polar"),

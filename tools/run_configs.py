@@ -121,6 +121,28 @@ def run_field_config(tag, name, n_rays, G, dev, world, rank, planes=None, n_chec
     return res
 
 
+def run_mirror_to_mirror(dev, n=700, n_check=192):
+    """The stage that dominates the reference's real workflow (CPU0402:283-301): the field on mirror 1
+    propagated to the hit points of mirror 2 -- an irregular detector set (no plane, no rows), so the
+    pair kernel's general loop runs."""
+    from akbraytracing_b200 import handoff, raytrace
+    coeffs, neg, plane, ray, src = workloads.chain_inputs("c3", n, dev)
+    tr = raytrace.trace_chain(coeffs, neg, plane, ray, src, want_dist=True)
+    m1, m2 = tr["points"][0], tr["points"][1]
+    k = 2.0 * np.pi / workloads.WAVELENGTH_EUV
+    w = dict(det_x=m2[0].contiguous(), det_y=m2[1].contiguous(), det_z=m2[2].contiguous(), src_x=m1[0].contiguous(),
+             src_y=m1[1].contiguous(), src_z=m1[2].contiguous(), u=handoff.opl_to_field(tr["dist"][0], k),
+             ds=handoff.calc_dS(m1, n, n).reshape(-1), k=k)
+    args = (w["det_x"], w["det_y"], w["det_z"], w["src_x"], w["src_y"], w["src_z"], w["u"], w["k"], w["ds"])
+    akb.fresnel_sum(*args)
+    ms, full = timed(lambda: akb.fresnel_sum(*args), reps=3)
+    terms = float(n * n) ** 2
+    err, same_peak = field_subset_parity(w, full, n_check)
+    return {"config": f"M2M: KB mirror 1 -> mirror 2 stage, {n * n} x {n * n} points (irregular detector set)",
+            "terms": terms, "n_gpus": 1, "ms": ms, "terms_per_s": terms / ms * 1e3, "rel_l2_vs_oracle_subset": err,
+            "subset": n_check, "subset_peak_pixel_same": same_peak}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="c1,c2,c3,c4")
@@ -144,6 +166,8 @@ def main():
             results.append(run_c2(dev))
         elif c == "c3" and rank == 0:
             results.append(run_field_config("c3", "C3: KB two-mirror trace 1e6 rays -> 512x512 grid", 1000, 512, dev, 1, 0))
+        elif c == "m2m" and rank == 0:
+            results.append(run_mirror_to_mirror(dev))
         elif c == "c4":
             G = args.c4_grid
             results.append(run_field_config("c4", f"C4: AKB four-mirror trace 1e6 rays x {G}x{G} detector", 1000, G, dev,
