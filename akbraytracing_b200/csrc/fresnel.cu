@@ -238,12 +238,9 @@ __device__ __forceinline__ double rcp_refined(double b)
     return fma_(y, e, y);
 }
 
-// phase A of a REFERENCED pair: (ex, ey, ez) = source - tile reference
-__device__ __forceinline__ PairA pair_phase_a_ref(const RefCtx &rc, double ex, double ey, double ez,
-                                                  const PhaseConst &pc, double magic)
+// phase A of a REFERENCED pair from ds = r^2 - r_ref^2
+__device__ __forceinline__ PairA pair_phase_a_ref_from_ds(const RefCtx &rc, double ds, const PhaseConst &pc, double magic)
 {
-    const double ax = add(ex, rc.gx), ay = add(ey, rc.gy), az = add(ez, rc.gz);
-    const double ds = fma_(ex, ax, fma_(ey, ay, mul(ez, az))); // r^2 - r_ref^2
     const double s = add(rc.s_ref, ds);
     PairA a;
     double rho;
@@ -254,6 +251,21 @@ __device__ __forceinline__ PairA pair_phase_a_ref(const RefCtx &rc, double ex, d
     a.p = fma_(fma_(-den, q, ds), y, q);                     // r - r_ref, correctly rounded quotient
     a.t = add(fma_(a.p, pc.q_hi, rc.phi), magic);            // MAGIC + rint((k (r - r_ref))/u + phi)
     return a;
+}
+
+// (ex, ey, ez) = source - tile reference; r^2 - r_ref^2 = sum_c e_c (e_c - 2 D_c)
+__device__ __forceinline__ PairA pair_phase_a_ref(const RefCtx &rc, double ex, double ey, double ez,
+                                                  const PhaseConst &pc, double magic)
+{
+    const double ax = add(ex, rc.gx), ay = add(ey, rc.gy), az = add(ez, rc.gz);
+    return pair_phase_a_ref_from_ds(rc, fma_(ex, ax, fma_(ey, ay, mul(ez, az))), pc, magic);
+}
+
+// planar-row block: xz = e_x (e_x - 2 D_x) + e_z (e_z - 2 D_z) is shared by the thread's points
+__device__ __forceinline__ PairA pair_phase_a_ref_row(const RefCtx &rc, double xz, double ey, const PhaseConst &pc,
+                                                      double magic)
+{
+    return pair_phase_a_ref_from_ds(rc, fma_(ey, add(ey, rc.gy), xz), pc, magic);
 }
 
 // r^2 -> (phase, 1/(2r), MAGIC + rint(phase/u))
@@ -421,7 +433,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
     // from the coordinates themselves (block-uniform vote), so irregular detector sets (mirror surfaces)
     // simply take the general loop.
     bool row = false;
-    if (!REF) {
+    {
         const long long i0 = (long long)blockIdx.x * THREADS * DPT;
         const double x0 = det_x[i0 < M ? i0 : M - 1];
         bool mine = true;
@@ -475,10 +487,10 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                     rc[d] = make_ref_ctx(X[d], Y[d], Z[d], T[ROWS * TILE + 0], T[ROWS * TILE + 1], T[ROWS * TILE + 2], pc,
                                          magic);
             }
-            if (ROW) { // the sx row becomes fl((x0 - sx)^2), CPU0402:76-77
+            if (ROW) { // the sx row becomes fl((x0 - sx)^2), CPU0402:76-77 (REFERENCED: e_x (e_x - 2 D_x))
                 for (int q = threadIdx.x; q < TILE; q += THREADS) {
-                    const double ddx = sub(X[0], T[q]);
-                    T[q] = mul(ddx, ddx);
+                    const double ddx = REF ? add(T[q], rc[0].gx) : sub(X[0], T[q]);
+                    T[q] = mul(REF ? T[q] : ddx, ddx);
                 }
                 // generic-proxy writes to a stage that a later bulk copy (async proxy) overwrites
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -507,8 +519,9 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                 if (ROW) {
 #pragma unroll
                     for (int q = 0; q < SPI; ++q) {
-                        ddz[q] = sub(Z[0], S[2][q]);
-                        dzz[q] = mul(ddz[q], ddz[q]);
+                        ddz[q] = REF ? add(S[2][q], rc[0].gz) : sub(Z[0], S[2][q]);
+                        dzz[q] = mul(REF ? S[2][q] : ddz[q], ddz[q]);
+                        if (REF) dzz[q] = add(S[0][q], dzz[q]); // the x and z terms of r^2 - r_ref^2
                     }
                 }
                 PairA a[NP];
@@ -520,7 +533,9 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
 #pragma unroll
                     for (int q = 0; q < SPI; ++q) {
                         const int i = SPI * d + q;
-                        if (REF) {
+                        if (REF && ROW) {
+                            a[i] = pair_phase_a_ref_row(rc[d], dzz[q], S[1][q], pc, S[5][q]);
+                        } else if (REF) {
                             a[i] = pair_phase_a_ref(rc[d], S[0][q], S[1][q], S[2][q], pc, S[5][q]);
                         } else if (ROW) {
                             a[i] = pair_phase_a_row<MODE>(S[0][q], Y[d], S[1][q], ddz[q], dzz[q], pc, S[5][q]);
@@ -678,6 +693,9 @@ const KernelEntry *kernel_table(int *count)
         make_entry<4, 512, 2, 1024, 3, 0>("dpt4 tile512x2 table1024 sincos 3 blocks/SM"),
         make_entry<1, 512, 2, 1024, 2, FORM_TAN | FORM_POLAR>("dpt1 tile512x2 table1024 tan polar"),
         make_entry<4, 512, 2, 2048, 2, FORM_TAN | FORM_POLAR>("dpt4 tile512x2 table2048 tan polar 2 blocks/SM"),
+        // REFERENCED keeps 7 more doubles per detector point in registers: 2 points per thread
+        make_entry<2, 256, 3, 4096, 2, FORM_TAN | FORM_POLAR | FORM_SHORTCOS>(
+            "dpt2 tile256x3 table4096 tan polar shortcos 2 blocks/SM"),
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));
     return entries;
@@ -694,8 +712,7 @@ const KernelEntry &selected_kernel(int mode, long long M = -1, long long N = -1,
         idx = (want >= 0 && want < n) ? want : -2;
     }
     if (idx >= 0) return e[idx];
-    // REFERENCED keeps 7 more doubles per detector point in registers: 2 points per thread
-    int pick = mode == AKB_PHASE_REFERENCED ? 1 : 0;
+    int pick = mode == AKB_PHASE_REFERENCED ? 5 : 0;
     // small problems (C1: 64x64 detector points x 1e4 sources): fewer points per thread so that
     // (detector blocks x source tiles) still covers every SM
     if (M >= 0 && N >= 0) {
