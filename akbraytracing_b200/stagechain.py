@@ -11,6 +11,13 @@ and stage chain: Wavecalc_raytrace_fromData_CPU0402.py:190-377):
     calculation_conditions.txt             "grid pix_y: ..", "grid pix_H1: ..", "option_AKB: ..", ...
     complex_data_<stage>.npz['data']       complex128 field per stage (output)
 
+Mirror order: the chain follows the FILE order M1 -> M2 -> M3 -> M4 exactly as the reference's reader
+does (CPU0402:276-328).  The reference's writer names the files in alternating order (M1 = vmirr_hyp,
+M2 = hmirr_hyp, M3 = vmirr_ell, M4 = hmirr_ell; BIG:13479, 13523-13554), which for the Wolter III+I
+layout is not the physical beam path.  This driver is deliberately bug-compatible: it
+reproduces what the reference computes from a given folder; a caller who wants the physical order
+passes ``mirror_clouds`` to ``write_handoff`` in that order.
+
 ``run_stage_chain`` walks source -> M1 -> M2 (-> M3 -> M4) -> Image -> Image2 with every field
 resident in HBM (one ``akb_fresnel_sum`` per stage, no file or host round trip in between) and
 writes the same ``complex_data_*.npz`` files.  ``write_handoff`` produces the folder from traced
