@@ -156,6 +156,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the JSON lines
         dist.init_process_group("nccl", device_id=dev)
     results = []
     for c in args.configs.split(","):
