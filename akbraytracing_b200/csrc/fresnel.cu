@@ -798,7 +798,9 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     int splits = 1;
     {
         double best = -1.0;
-        const int max_splits = tiles_total < 64 ? tiles_total : 64;
+        int max_splits = tiles_total < 64 ? tiles_total : 64;
+        const long long by_memory = (2LL << 30) / (16 * M); // partial sums [split][M] stay below 2 GiB
+        if (max_splits > by_memory) max_splits = by_memory < 1 ? 1 : (int)by_memory;
         for (int s = 1; s <= max_splits; ++s) {
             const int tps = (tiles_total + s - 1) / s;
             const int s_eff = (tiles_total + tps - 1) / tps;
@@ -808,11 +810,13 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
             double eff = waves / full;
             // the last split may hold fewer tiles: account for the imbalance
             eff *= (double)tiles_total / ((double)tps * s);
-            if (eff > best + 0.02) {
+            // every split costs a table build per block and one more partial sum per detector point:
+            // prefer fewer splits unless more of them fill the last wave measurably better
+            eff -= 2.0e-4 * s;
+            if (eff > best) {
                 best = eff;
                 splits = s;
             }
-            if (eff >= 0.97) break;
         }
     }
     int tiles_per_split = (tiles_total + splits - 1) / splits;
