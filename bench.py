@@ -127,6 +127,15 @@ def cpu_workload(n_rays=RAYS):
                 src_z=np.ascontiguousarray(last[2]), u=u, ds=ds, k=k)
 
 
+def host_threads():
+    """Every host core this process may run on.  torch.distributed.run exports OMP_NUM_THREADS=1 to its
+    workers; the CPU arm must not inherit that (it would time ONE thread), so the count is passed explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def time_cpu_sample(w, n_det, threads, rng_seed=0):
     import oracle
     sel = np.sort(np.random.default_rng(rng_seed).choice(w["det_x"].shape[0], n_det, replace=False))
@@ -141,7 +150,7 @@ def cpu_baseline(target_s=12.0):
     """Oracle port (C + OpenMP, all host threads) on a bounded detector subset of the C3 stage."""
     import oracle
     oracle.build()
-    threads = oracle.max_threads()
+    threads = host_threads()
     w = cpu_workload()
     time_cpu_sample(w, max(threads, 16), threads)            # warms the thread pool
     rate, _ = time_cpu_sample(w, 4 * max(threads, 16), threads)  # calibration
@@ -159,7 +168,7 @@ def run_reference(args):
         return
     import oracle
     oracle.build()
-    threads = oracle.max_threads()
+    threads = host_threads()
     w = cpu_workload()
     n_src = w["src_x"].shape[0]
     time_cpu_sample(w, max(threads, 16), threads)
@@ -214,8 +223,18 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: library banners printed while the communicator comes up
+        # (NCCL_DEBUG=VERSION on some boxes) are sent to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     L = _lib.load()
 
     def barrier():

@@ -156,8 +156,15 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the JSON lines
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)  # library banners (NCCL_DEBUG=VERSION) go to stderr, stdout keeps the JSON lines
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     results = []
     for c in args.configs.split(","):
         c = c.strip().lower()
