@@ -343,9 +343,10 @@ def run_ours(args):
             "kernel": "fresnel_pairs_kernel<faithful> [%s]" % L.akb_fresnel_variant_name().decode(), "bound": "fp64",
             "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of THIS launch (1e6 sources x 512x512 detectors,
-            # 8 source splits) from ncu --set full: profiles/r01b_ncu_full_bench_launch.md (57.2 MB + 13.5 MB).
-            # Algorithmic bytes: 48 MB packed sources + 6.3 MB detector xyz + 33.5 MB partial sums (L2-resident).
-            "traffic": 70.7e6 if world == 1 else None, "traffic_unit": "bytes per launch (ncu, round 1)",
+            # 15 source splits) from ncu --set full: profiles/r01h_ncu_full_bench_launch.md (57.7 MB + 24.7 MB).
+            # Algorithmic bytes: 48 MB packed sources + 6.3 MB detector xyz + 63 MB partial sums (mostly L2-resident
+            # until the reduction kernel consumes them).
+            "traffic": 82.3e6 if world == 1 else None, "traffic_unit": "bytes per launch (ncu, round 1)",
             "peak_source": "on-box DFMA microbenchmark (akb_fp64_peak_probe, measured in this run); "
                            "MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
             "algorithmic_flop_per_term": ALG_FLOP_PER_TERM,
