@@ -688,10 +688,11 @@ const KernelEntry *kernel_table(int *count)
         // multiple of 4 warps lose 10-20 %, one 640/768-thread block per SM sharing one table loses 2-4 %)
         make_entry<4, 256, 3, 4096, 2, FORM_TAN | FORM_POLAR | FORM_SHORTCOS>(
             "dpt4 tile256x3 table4096 tan polar shortcos 2 blocks/SM"),
-        make_entry<2, 512, 2, 1024, 2, FORM_TAN | FORM_POLAR>("dpt2 tile512x2 table1024 tan polar"),
+        // small problems: fewer points per thread, and a 2048-entry table (8 sincospi per thread and block)
+        make_entry<2, 256, 3, 2048, 2, FORM_TAN | FORM_POLAR>("dpt2 tile256x3 table2048 tan polar"),
         // the round-1 formulation (sin/cos polynomials, complex weights), kept for A/B runs
         make_entry<4, 512, 2, 1024, 3, 0>("dpt4 tile512x2 table1024 sincos 3 blocks/SM"),
-        make_entry<1, 512, 2, 1024, 2, FORM_TAN | FORM_POLAR>("dpt1 tile512x2 table1024 tan polar"),
+        make_entry<1, 128, 4, 2048, 2, FORM_TAN | FORM_POLAR>("dpt1 tile128x4 table2048 tan polar"),
         make_entry<4, 512, 2, 2048, 2, FORM_TAN | FORM_POLAR>("dpt4 tile512x2 table2048 tan polar 2 blocks/SM"),
         // REFERENCED keeps 7 more doubles per detector point in registers: 2 points per thread
         make_entry<2, 256, 3, 4096, 2, FORM_TAN | FORM_POLAR | FORM_SHORTCOS>(
@@ -699,6 +700,55 @@ const KernelEntry *kernel_table(int *count)
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));
     return entries;
+}
+
+// Split the source tiles of one launch so that the grid (detector blocks x splits) fills whole waves of
+// `slots` resident blocks.  Returns the split count; *eff_out = fraction of the slots x time rectangle
+// that does work (wave quantisation x imbalance of the last split).
+int plan_splits(long long blocks_x, int tiles_total, long long slots, long long M, double *eff_out)
+{
+    int splits = 1;
+    double best = -1.0, best_raw = 0.0;
+    int max_splits = tiles_total < 64 ? tiles_total : 64;
+    const long long by_memory = (2LL << 30) / (16 * (M > 0 ? M : 1)); // partial sums [split][M] stay below 2 GiB
+    if (max_splits > by_memory) max_splits = by_memory < 1 ? 1 : (int)by_memory;
+    for (int s = 1; s <= max_splits; ++s) {
+        const int tps = (tiles_total + s - 1) / s;
+        const int s_eff = (tiles_total + tps - 1) / tps;
+        if (s_eff != s) continue;
+        const double waves = (double)(blocks_x * s) / (double)slots;
+        const double full = waves <= 1.0 ? 1.0 : (double)(long long)(waves + 0.999999);
+        double eff = waves / full;
+        eff *= (double)tiles_total / ((double)tps * s); // the last split may hold fewer tiles
+        // every split costs a table build per block and one more partial sum per detector point:
+        // prefer fewer splits unless more of them fill the last wave measurably better
+        const double score = eff - 2.0e-4 * s;
+        if (score > best) {
+            best = score;
+            best_raw = eff;
+            splits = s;
+        }
+    }
+    if (eff_out) *eff_out = best_raw;
+    return splits;
+}
+
+// resident blocks per SM of a variant (occupancy query, cached: every device of a box is the same part)
+int resident_blocks(const KernelEntry &ke, int mode)
+{
+    static int cache[16][3]; // 0 = not asked yet
+    int n = 0;
+    const KernelEntry *e = kernel_table(&n);
+    const int v = (int)(&ke - e);
+    if (v >= 0 && v < 16 && cache[v][mode] > 0) return cache[v][mode];
+    int per_sm = 1;
+    if (cudaFuncSetAttribute(ke.fn[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, ke.smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke.fn[mode], ke.threads, ke.smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    if (v >= 0 && v < 16) cache[v][mode] = per_sm;
+    return per_sm;
 }
 
 const KernelEntry &selected_kernel(int mode, long long M = -1, long long N = -1, int sms = 148)
@@ -713,15 +763,24 @@ const KernelEntry &selected_kernel(int mode, long long M = -1, long long N = -1,
     }
     if (idx >= 0) return e[idx];
     int pick = mode == AKB_PHASE_REFERENCED ? 5 : 0;
-    // small problems (C1: 64x64 detector points x 1e4 sources): fewer points per thread so that
-    // (detector blocks x source tiles) still covers every SM
-    if (M >= 0 && N >= 0) {
-        const int order[3] = {pick, 1, 3}; // 4 (or 2), 2, 1 points per thread
+    // Small problems (C1: 64x64 detector points x 1e4 sources) cannot fill the SMs with 4 points per thread:
+    // among the 4 / 2 / 1 points-per-thread variants take the one with the lowest estimated time,
+    // FP64 instructions per pair / wave-fill efficiency of its best split plan.
+    if (M > 0 && N > 0) {
+        const int order[3] = {pick, 1, 3};
+        const double instr[3] = {31.0, 32.0, 32.0};
+        double best = 1e300;
         for (int o = 0; o < 3; ++o) {
-            pick = order[o];
-            const long long blocks = (M + e[pick].threads * e[pick].dpt - 1) / (e[pick].threads * e[pick].dpt);
-            const long long tiles = (N + e[pick].tile - 1) / e[pick].tile;
-            if (blocks * tiles >= 2LL * sms || e[pick].dpt == 1) break;
+            const KernelEntry &c = e[order[o]];
+            const long long blocks = (M + c.threads * c.dpt - 1) / (c.threads * c.dpt);
+            const long long tiles = (N + c.tile - 1) / c.tile;
+            double eff = 0.0;
+            plan_splits(blocks, (int)(tiles < (1LL << 30) ? tiles : (1LL << 30)), (long long)sms * resident_blocks(c, mode), M, &eff);
+            const double cost = instr[o] / (eff > 1e-6 ? eff : 1e-6);
+            if (cost < best * 0.97) { // a smaller variant must win by 3 %
+                best = cost;
+                pick = order[o];
+            }
         }
     }
     return e[pick];
@@ -789,36 +848,12 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     const long long n_padded = (N + 1) & ~1LL;
 
     // ---- plan: split the source tiles so the grid fills whole waves
-    int per_sm = 1;
+    // (the attribute is per device: set it on every call, the occupancy figure itself is cached)
     AKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ke.smem));
-    AKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ke.threads, ke.smem));
-    if (per_sm < 1) per_sm = 1;
+    const int per_sm = resident_blocks(ke, mode);
     const long long slots = (long long)sms * per_sm;
     const long long blocks_x = (M + ke.threads * ke.dpt - 1) / (ke.threads * ke.dpt);
-    int splits = 1;
-    {
-        double best = -1.0;
-        int max_splits = tiles_total < 64 ? tiles_total : 64;
-        const long long by_memory = (2LL << 30) / (16 * M); // partial sums [split][M] stay below 2 GiB
-        if (max_splits > by_memory) max_splits = by_memory < 1 ? 1 : (int)by_memory;
-        for (int s = 1; s <= max_splits; ++s) {
-            const int tps = (tiles_total + s - 1) / s;
-            const int s_eff = (tiles_total + tps - 1) / tps;
-            if (s_eff != s) continue;
-            const double waves = (double)(blocks_x * s) / (double)slots;
-            const double full = waves <= 1.0 ? 1.0 : (double)(long long)(waves + 0.999999);
-            double eff = waves / full;
-            // the last split may hold fewer tiles: account for the imbalance
-            eff *= (double)tiles_total / ((double)tps * s);
-            // every split costs a table build per block and one more partial sum per detector point:
-            // prefer fewer splits unless more of them fill the last wave measurably better
-            eff -= 2.0e-4 * s;
-            if (eff > best) {
-                best = eff;
-                splits = s;
-            }
-        }
-    }
+    const int splits = plan_splits(blocks_x, tiles_total, slots, M, nullptr);
     int tiles_per_split = (tiles_total + splits - 1) / splits;
 
     int rc;
