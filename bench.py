@@ -450,7 +450,22 @@ def bench_ray_c2(akb, workloads, torch, dev, peaks, peak_src, n=3163, reps=5):
     ms, bpr = times[True]
     gbs = N * bpr / (ms * 1e-3) / 1e9
     ms2, bpr2 = times[False]
+    # the reference's NumPy path (ER3D:18-71 via ell.calc_reflect, ER3D:241-245) restated op for op in
+    # oracle/numpy_port.py, on the first 1e6 rays of the same bundle, one host thread (NumPy elementwise
+    # code is single-threaded in the reference too)
+    from oracle import numpy_port
+    n_cpu = min(N, 1_000_000)
+    rh, sh = ray[:, :n_cpu].cpu().numpy(), src[:, :n_cpu].cpu().numpy()
+    coh = np.asarray(co, dtype=np.float64)
+    t0 = time.perf_counter()
+    ph = numpy_port.mirr_ray_intersection(coh, rh, sh)
+    nh = numpy_port.norm_vector(coh, ph)
+    numpy_port.reflect_ray(rh, nh)
+    cpu_s = time.perf_counter() - t0
+    cpu = {"value": n_cpu / cpu_s, "unit": "rays/s", "cores": 1, "kind": "port",
+           "sample": f"first {n_cpu} rays of the C2 bundle, oracle/numpy_port.py (NumPy restatement of ER3D:18-71), {cpu_s:.2f} s"}
     return {"kernel": "intersect_reflect_kernel<2, normal>", "workload": f"C2: {N} rays, single elliptical mirror",
+            "cpu_baseline": cpu,
             "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
             "traffic": None, "peak_source": peak_src, "bytes_per_ray": bpr, "rays_per_s": N / (ms * 1e-3),
             "kernel_ms": ms, "without_normal": {"bytes_per_ray": bpr2, "kernel_ms": ms2,
