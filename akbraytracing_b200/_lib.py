@@ -35,6 +35,7 @@ SIGNATURES = {
     "akb_shard_range": (_c_int, [_c_i64, _c_int, _c_int, ctypes.POINTER(_c_i64), ctypes.POINTER(_c_i64)]),
     "akb_launch_count": (_c_i64, [_c_int]),
     "akb_fresnel_variant_name": (ctypes.c_char_p, []),
+    "akb_fresnel_row_blocks": (_c_int, [ctypes.POINTER(ctypes.c_int64), _c_int]),
     "akb_fresnel_timing": (_c_int, [_c_int]),
     "akb_fresnel_last_timing": (_c_int, [ctypes.POINTER(_c_dbl), ctypes.POINTER(_c_dbl), ctypes.POINTER(_c_int),
                                           ctypes.POINTER(_c_i64), ctypes.POINTER(_c_int)]),

@@ -139,6 +139,9 @@ __device__ __forceinline__ void tma_bulk_load(uint32_t dst, const void *src, uin
                  : "memory");
 }
 
+// blocks that took the planar-row loop (test / measurement aid, akb_fresnel_row_blocks)
+__device__ unsigned long long g_row_blocks;
+
 // ---------------------------------------------------------------- constants
 // FP64 constants live in constant memory so that they reach the DFMA as a c[bank][offset] /
 // uniform-register operand: as literals ptxas re-materialises each of them with two UMOVs per
@@ -440,6 +443,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
 #pragma unroll
         for (int d = 0; d < DPT; ++d) mine = mine && X[d] == x0 && Z[d] == Z[0];
         row = __syncthreads_and(mine);
+        if (row && threadIdx.x == 0) atomicAdd(&g_row_blocks, 1ULL);
     }
 
     for (int m = threadIdx.x; m < TBL; m += THREADS) {
@@ -919,6 +923,18 @@ extern "C" int akb_fresnel_last_timing(double *pairs_ms, double *total_ms, int *
     if (splits) *splits = g_timing.splits;
     if (blocks_x) *blocks_x = g_timing.blocks_x;
     if (blocks_per_sm) *blocks_per_sm = g_timing.per_sm;
+    return AKB_OK;
+}
+
+extern "C" int akb_fresnel_row_blocks(int64_t *row_blocks, int reset)
+{
+    unsigned long long v = 0;
+    AKB_CUDA(cudaMemcpyFromSymbol(&v, g_row_blocks, sizeof(v))); // synchronises with the device
+    if (row_blocks) *row_blocks = (int64_t)v;
+    if (reset) {
+        v = 0;
+        AKB_CUDA(cudaMemcpyToSymbol(g_row_blocks, &v, sizeof(v)));
+    }
     return AKB_OK;
 }
 

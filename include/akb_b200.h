@@ -99,6 +99,11 @@ int akb_fresnel_timing(int enable);
 int akb_fresnel_last_timing(double *pairs_ms, double *total_ms, int *splits, int64_t *blocks_x,
                             int *blocks_per_sm);
 
+/* Test / measurement aid: number of pair-kernel blocks on the current device that found their detector
+ * points on a plane x = const with rows aligned to the threads ("planar-row" loop)
+ * since the last reset.  Synchronises with the device. */
+int akb_fresnel_row_blocks(int64_t *row_blocks, int reset);
+
 /* name of the pair-kernel variant in use (default, or chosen with AKB_FRESNEL_VARIANT=<n>) */
 const char *akb_fresnel_variant_name(void);
 

@@ -182,35 +182,54 @@ def test_fresnel_weight_phases_and_magnitudes(akb, M, N):
     assert not np.isfinite(oracle.fresnel_sum(x[:4], y[:4], z[:4], sx, sy, sz, ub, k, ds)).any()
 
 
-@pytest.mark.parametrize("G,H", [(64, 64), (512, 12), (100, 37), (30, 30)])
-def test_fresnel_planar_row_blocks_match_general_loop_bitwise(akb, G, H):
+def _row_blocks(akb):
+    """Blocks that took the planar-row loop since the last call (and reset)."""
+    import ctypes
+    rows = ctypes.c_int64()
+    akb._lib.check(akb._lib.load().akb_fresnel_row_blocks(ctypes.byref(rows), 1), "akb_fresnel_row_blocks")
+    return rows.value
+
+
+@pytest.mark.parametrize("G,H,N", [(64, 64, 3001), (512, 12, 3001), (100, 37, 3001), (30, 30, 3001), (512, 512, 20001)])
+def test_fresnel_planar_row_blocks_match_general_loop_bitwise(akb, G, H, N):
     """Blocks whose detector points share x and (per thread) z take a specialised loop that forms
     (x - X)^2 once per source and (z - Z)^2 once per (thread, source).  The same points in shuffled
-    order take the general loop: the two must agree BIT FOR BIT (same operations in the same order), for
-    grids whose rows do / do not align with the 4 points of a thread, and both against the oracle."""
+    order take the general loop (4 points per thread: their z differ): the two must agree BIT FOR BIT
+    (same operations in the same order), for grids whose rows do / do not align with the points of a
+    thread, and both against the oracle.  The 512 x 512 case is large enough for the 4-points-per-thread
+    kernel: there the block counter proves that the ordered grid ran the planar-row loop in EVERY block
+    and the shuffled set in NONE."""
     rng = np.random.default_rng(G * 1000 + H)
     yy, zz = np.meshgrid(np.linspace(-1e-6, 1e-6, G) + 3e-4, np.linspace(-1e-6, 1e-6, H) - 2e-4)
     x = np.full(G * H, 0.15); y = yy.ravel(); z = zz.ravel()
-    N = 3001
     sx = rng.uniform(-1e-2, 1e-2, N); sy = rng.uniform(-1e-3, 1e-3, N); sz = rng.uniform(-1e-3, 1e-3, N)
     u = np.exp(2j * np.pi * rng.uniform(size=N)); ds = rng.uniform(1e-9, 2e-9, N)
     k = 2 * np.pi / 13.5e-9
     perm = rng.permutation(G * H)
-    ref = oracle.fresnel_sum(x, y, z, sx, sy, sz, u, k, ds)
+    sel = np.sort(rng.choice(G * H, min(G * H, 2048), replace=False))  # oracle subset (all points when small)
+    ref = oracle.fresnel_sum(x[sel], y[sel], z[sel], sx, sy, sz, u, k, ds)
+    big = G * H >= 512 * 512
+    _row_blocks(akb)  # reset
     for mode in (akb.PHASE_FAITHFUL, akb.PHASE_EXACT):
         grid = akb.fresnel_sum(x, y, z, sx, sy, sz, u, k, ds, mode=mode)
+        took_row = _row_blocks(akb)
         shuffled = akb.fresnel_sum(x[perm], y[perm], z[perm], sx, sy, sz, u, k, ds, mode=mode)
+        took_general = _row_blocks(akb)
+        if big:  # 4 points per thread, 1024 per block
+            print(f"mode {mode}: planar-row blocks: ordered grid {took_row}, shuffled {took_general}")
+            assert took_row > 0 and took_row % (G * H // 1024) == 0 and took_general == 0
         assert np.array_equal(grid[perm], shuffled), f"mode {mode}: planar-row loop differs from the general loop"
-        assert rel_l2(grid, ref) <= (1e-12 if mode == akb.PHASE_FAITHFUL else FIELD_TOL / 10)
+        assert rel_l2(grid[sel], ref) <= (1e-12 if mode == akb.PHASE_FAITHFUL else FIELD_TOL / 10)
     # REFERENCED has its own planar-row form (x and z terms of r^2 - r_ref^2 shared); a different summation
     # order of that difference, so equal only to the mode's own accuracy (~1e-9)
     grid = akb.fresnel_sum(x, y, z, sx, sy, sz, u, k, ds, mode=akb.PHASE_REFERENCED)
     shuffled = akb.fresnel_sum(x[perm], y[perm], z[perm], sx, sy, sz, u, k, ds, mode=akb.PHASE_REFERENCED)
-    assert rel_l2(grid[perm], shuffled) <= 1e-8 and rel_l2(grid, ref) <= FIELD_TOL / 10
-    # a plane that is constant in z within threads but NOT in x: general loop, still right
-    x2 = x + np.repeat(np.linspace(0, 1e-6, H), G)
-    got = akb.fresnel_sum(x2, y, z, sx, sy, sz, u, k, ds)
-    assert rel_l2(got, oracle.fresnel_sum(x2, y, z, sx, sy, sz, u, k, ds)) <= 1e-12
+    assert rel_l2(grid[perm], shuffled) <= 1e-8 and rel_l2(grid[sel], ref) <= FIELD_TOL / 10
+    if not big:
+        # a plane that is constant in z within threads but NOT in x: general loop, still right
+        x2 = x + np.repeat(np.linspace(0, 1e-6, H), G)
+        got = akb.fresnel_sum(x2, y, z, sx, sy, sz, u, k, ds)
+        assert rel_l2(got[sel], oracle.fresnel_sum(x2[sel], y[sel], z[sel], sx, sy, sz, u, k, ds)) <= 1e-12
 
 
 def test_fresnel_empty_inputs(akb):
