@@ -837,7 +837,7 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
         return AKB_OK;
     }
     AKB_REQUIRE(src_x && src_y && src_z && src_u, "source pointers must not be NULL");
-    AKB_REQUIRE(k >= 0.0 && k < 1.0e12, "wave number k must be in [0, 1e12) (k*r must stay below 2^48 units)");
+    AKB_REQUIRE(k >= 0.0 && k < 1.0e12, "wave number k must be in [0, 1e12) (k*r must stay below 3.4e12 rad: 2^51 table steps)");
 
     int device = 0;
     AKB_CUDA(cudaGetDevice(&device));
@@ -867,10 +867,19 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     g_timing.blocks_x = blocks_x;
     if ((rc = timing_mark(0, st))) return rc;
 
-    double *packed = nullptr, *partial = nullptr;
+    // stream-ordered scratch, handed back to the pool on every exit path (also the error returns)
+    struct Scratch {
+        cudaStream_t st;
+        double *p = nullptr;
+        ~Scratch()
+        {
+            if (p) cudaFreeAsync(p, st);
+        }
+    } packed_s{st}, partial_s{st};
     const int rows = rows_of(ke.form);
-    AKB_CUDA(cudaMallocAsync(&packed, (size_t)tiles_total * (rows * TILE + HEAD) * sizeof(double), st));
-    if (splits > 1) AKB_CUDA(cudaMallocAsync(&partial, (size_t)splits * M * 2 * sizeof(double), st));
+    AKB_CUDA(cudaMallocAsync(&packed_s.p, (size_t)tiles_total * (rows * TILE + HEAD) * sizeof(double), st));
+    if (splits > 1) AKB_CUDA(cudaMallocAsync(&partial_s.p, (size_t)splits * M * 2 * sizeof(double), st));
+    double *const packed = packed_s.p, *const partial = partial_s.p;
 
     PhaseConst pc = make_phase_const(k, ke.table);
     pack_sources_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, st>>>(
@@ -895,9 +904,7 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
         reduce_partials_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(
             reinterpret_cast<const double2 *>(partial), splits, M, reinterpret_cast<double2 *>(out));
         AKB_LAUNCH_CHECK();
-        AKB_CUDA(cudaFreeAsync(partial, st));
     }
-    AKB_CUDA(cudaFreeAsync(packed, st));
     if ((rc = timing_mark(3, st))) return rc;
     g_timing.valid = g_timing.enabled;
     return AKB_OK;

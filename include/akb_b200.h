@@ -72,8 +72,9 @@ int akb_device_count(void);
  *   src_ds     float64[N] or NULL (= 1)
  *   out        complex128[M]
  *   mode       AKB_PHASE_FAITHFUL | AKB_PHASE_EXACT | AKB_PHASE_REFERENCED
- * Domain: 0 <= k < 1e12 and k*r < 1.4e13 rad for every pair (the phase is reduced exactly as an integer
- * multiple of 2*pi/1024 below 2^51); beyond that the result is undefined.  r = 0 yields NaN/inf like the
+ * Domain: 0 <= k < 1e12 and k*r < 3.4e12 rad for every pair (the phase is reduced exactly as an integer
+ * multiple of 2*pi/4096 below 2^51; the reference's largest stage, 146 m at 1.35 nm, is 6.8e11 rad);
+ * beyond that the result is undefined.  r = 0 yields NaN/inf like the
  * reference.  The summation order over j differs from the reference's (tiles, fixed-order partial sums):
  * results are bit-reproducible run to run and agree with the reference to ~1e-13 relative L2.
  */
