@@ -373,6 +373,20 @@ def run_ours(args):
                                                         torch.linalg.vector_norm(g_ref))}
         del g_out
         torch.cuda.empty_cache()
+        # the two non-default phase modes on this rank's block of the same stage (one warm-up, one timed pass each)
+        ref_field = out[sl] if world > 1 else out
+        phase_modes = {}
+        for mode_name, mode_id in (("exact", akb.PHASE_EXACT), ("referenced", akb.PHASE_REFERENCED)):
+            for rep_i in range(2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fm = akb.fresnel_sum(dx, dy, dz, last[0], last[1], last[2], u, k, ds, mode=mode_id)
+                e1.record()
+                torch.cuda.synchronize()
+            phase_modes[mode_name] = {
+                "terms_per_s": float(RAYS * RAYS) * count / (e0.elapsed_time(e1) * 1e-3),
+                "rel_l2_vs_faithful": float(torch.linalg.vector_norm(fm - ref_field) / torch.linalg.vector_norm(ref_field))}
+        del fm
         # secondary line: the HBM-bound ray kernel at config C2 (1e7 rays, one mirror)
         ray_roof = bench_ray_c2(akb, workloads, torch, dev, peaks, peak_src)
         result = {
@@ -385,7 +399,7 @@ def run_ours(args):
                     "timer": "host wall clock around the synchronous call, max over ranks",
                     "steps": e2e_steps, "max_abs_diff_vs_device_path": same},
             "gpu_launches": int(launches) * world, "roofline": roofline, "roofline_ray": ray_roof,
-            "gpu_baseline": gpu_baseline,
+            "gpu_baseline": gpu_baseline, "phase_modes": phase_modes,
         }
     if world > 1:
         dist.barrier()
