@@ -24,6 +24,9 @@ KEYS = [
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
     "smsp__average_warp_latency_per_inst_issued.ratio",
+    "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed",
+    "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed",
+    "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed",
 ]
 STALL = "smsp__average_warps_issue_stalled_"
 with open(out, "w") as fh:
@@ -38,6 +41,17 @@ with open(out, "w") as fh:
                 fh.write(f"| {k} | {d[k]} | {u[k]} |\n")
         stalls = sorted(((float(d[h]), h[len(STALL):].replace('_per_issue_active.ratio', '')) for h in hdr
                          if h.startswith(STALL) and d[h] not in ("", "n/a")), reverse=True)
+        try:  # executed FP64 flop/s from the SASS op counters (2*dfma + dmul + dadd)
+            f = lambda n: float(d[f"smsp__sass_thread_inst_executed_op_{n}_pred_on.sum.per_cycle_elapsed"].replace(",", ""))
+            hz = float(d["sm__cycles_elapsed.avg.per_second"].replace(",", "")) * {"Ghz": 1e9, "Mhz": 1e6, "hz": 1.0}.get(
+                u["sm__cycles_elapsed.avg.per_second"], 1e9)
+            per_cycle = 2 * f("dfma") + f("dmul") + f("dadd")
+            lanes = f("dfma") + f("dmul") + f("dadd")
+            fh.write(f"\nexecuted FP64 work from the op counters: {per_cycle:.1f} flop/cycle = {per_cycle * hz / 1e12:.2f} TFLOP/s "
+                     f"(2*dfma + dmul + dadd); {lanes:.1f} FP64 thread-instructions/cycle of the GPU's "
+                     f"148 SM x 64 lanes = {100 * lanes / (148 * 64):.1f} % of the FP64 lanes\n")
+        except (KeyError, ValueError):
+            pass
         fh.write("\nwarp stall reasons (warps per issue-active cycle): " +
                  ", ".join(f"{n} {v:.2f}" for v, n in stalls[:7]) + "\n")
 print("wrote", out)
