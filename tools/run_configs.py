@@ -121,6 +121,36 @@ def run_field_config(tag, name, n_rays, G, dev, world, rank, planes=None, n_chec
     return res
 
 
+def run_trace(tag, name, dev, n=1000, n_cpu=200_000):
+    """The ray part of C3 / C4 alone: K mirrors + detector plane + segment lengths for n*n rays in ONE kernel
+    (BIG:11039-11054 / BIG:2881-2905), next to the reference's NumPy call sequence restated in
+    oracle/numpy_port.py on the first n_cpu rays (one host thread), with a bit-for-bit check on that subset."""
+    from oracle import numpy_port
+    from akbraytracing_b200 import raytrace
+    coeffs, neg, plane, ray, src = workloads.chain_inputs(tag, n, dev)
+    K = len(neg)
+    raytrace.trace_chain(coeffs, neg, plane, ray, src, check=False)
+    ms, tr = timed(lambda: raytrace.trace_chain(coeffs, neg, plane, ray, src, check=False), reps=5)
+    N = ray.shape[1]
+    rh, sh = ray[:, :n_cpu].cpu().numpy(), src[:, :n_cpu].cpu().numpy()
+    t0 = time.perf_counter()
+    cur_r, cur_s, pts = rh, sh, []
+    for co, ng in zip(coeffs, neg):
+        p = numpy_port.mirr_ray_intersection(np.asarray(co), cur_r, cur_s, ng)
+        nv = numpy_port.norm_vector(np.asarray(co), p)
+        cur_r, cur_s = numpy_port.reflect_ray(cur_r, nv), p
+        pts.append(p)
+    det = numpy_port.plane_ray_intersection(np.asarray(plane), cur_r, cur_s)
+    cpu_s = time.perf_counter() - t0
+    same = bool(np.array_equal(tr["det"][:, :n_cpu].cpu().numpy(), det) and
+                all(np.array_equal(tr["points"][i][:, :n_cpu].cpu().numpy(), pts[i]) for i in range(K)))
+    bytes_per_ray = 48 + 24 * K + 24 + 24 + 8 * K  # in, K hit points, final direction, detector point, K lengths
+    return {"config": name, "rays": N, "mirrors": K, "ms": ms, "rays_per_s": N / ms * 1e3,
+            "GB_per_s": N * bytes_per_ray / ms / 1e6, "bytes_per_ray": bytes_per_ray,
+            "cpu_numpy_rays_per_s_1_thread": n_cpu / cpu_s, "cpu_sample_rays": n_cpu,
+            "subset_bit_identical_to_numpy_restatement": same}
+
+
 def run_mirror_to_mirror(dev, n=700, n_check=192):
     """The stage that dominates the reference's real workflow (CPU0402:283-301): the field on mirror 1
     propagated to the hit points of mirror 2 -- an irregular detector set (no plane, no rows), so the
@@ -174,6 +204,10 @@ def main():
             results.append(run_c2(dev))
         elif c == "c3" and rank == 0:
             results.append(run_field_config("c3", "C3: KB two-mirror trace 1e6 rays -> 512x512 grid", 1000, 512, dev, 1, 0))
+        elif c == "c3t" and rank == 0:
+            results.append(run_trace("c3", "C3 trace: KB two mirrors + plane, 1e6 rays, one fused kernel", dev))
+        elif c == "c4t" and rank == 0:
+            results.append(run_trace("c4", "C4 trace: AKB four mirrors + plane, 1e6 rays, one fused kernel", dev))
         elif c == "m2m" and rank == 0:
             results.append(run_mirror_to_mirror(dev))
         elif c == "c4":
