@@ -173,7 +173,8 @@ def run_reference(args):
     n_src = w["src_x"].shape[0]
     time_cpu_sample(w, max(threads, 16), threads)
     rate, _ = time_cpu_sample(w, 4 * max(threads, 16), threads)
-    n_det = int(max(threads, rate * 4.0 / n_src))  # ~4 s per step
+    step_s = float(os.environ.get("AKB_BENCH_REF_STEP_S", "4.0"))  # CPU seconds per step (tests shorten it)
+    n_det = int(max(threads, rate * step_s / n_src))
     n_det = min(GRID * GRID, max(threads, (n_det // threads) * threads))
     for i in range(args.warmup):
         time_cpu_sample(w, n_det, threads, rng_seed=100 + i)

@@ -1,0 +1,40 @@
+"""CPU-only check of bench.py's reference arm (the one leg of the benchmark that needs no GPU): it must
+print exactly one JSON line on stdout carrying the keys the driver reads, time the CPU restatement with
+every host core even when OMP_NUM_THREADS=1 is exported (torch.distributed.run does that), and stay silent
+on ranks other than 0."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(extra_env, *args):
+    env = dict(os.environ, AKB_BENCH_REF_STEP_S="0.3", **extra_env)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3",
+                        *args], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p.stdout
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    out = _run({"OMP_NUM_THREADS": "1"})
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1, out
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "fresnel_terms_per_s" and d["unit"] == "terms/s"
+    assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["vs_baseline"] is None and d["n_gpus"] == 1
+    assert d["steps"] == 1 and d["warmup"] == 3 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["workload"].startswith("C3") and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["unit"] == "terms/s" and cb["sample"]
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    assert cb["cores"] == ncores  # not the single thread OMP_NUM_THREADS=1 would give
+    assert d["e2e"] == {"value": d["value"], "unit": "terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
+
+
+def test_reference_arm_is_silent_on_other_ranks():
+    out = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2")
+    assert out.strip() == ""
