@@ -1,4 +1,4 @@
-"""CPU-only check of bench.py's reference arm (the one leg of the benchmark that needs no GPU): it must
+"""bench.py contract checks.  CPU: the reference arm (the one leg of the benchmark that needs no GPU): it must
 print exactly one JSON line on stdout carrying the keys the driver reads, time the CPU restatement with
 every host core even when OMP_NUM_THREADS=1 is exported (torch.distributed.run does that), and stay silent
 on ranks other than 0."""
@@ -38,3 +38,32 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 def test_reference_arm_is_silent_on_other_ranks():
     out = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2")
     assert out.strip() == ""
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_our_arm_prints_one_json_line_with_the_contract_keys():
+    """The GPU arm on one device (1 timed step, CPU baseline skipped to keep the test short)."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--no-cpu-baseline"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, p.stdout
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+        assert key in d, key
+    assert d["metric"] == "fresnel_terms_per_s" and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["dtype"] == "f64"
+    assert d["value"] > 1e11 and d["gpu_launches"] > 0  # the CUDA path ran (a CPU fallback could not reach 1e11 terms/s)
+    r = d["roofline"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in r, key
+    assert 0.0 < r["frac"] < 1.0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert 0.9 < r["kernel_share_of_step"] <= 1.0
+    e = d["e2e"]
+    assert e["value"] > 1e11 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert e["max_abs_diff_vs_device_path"] == 0.0  # host-buffer call and device call: the same bits
+    assert d["gpu_baseline"]["rel_l2_vs_fused_kernel"] < 1e-9
+    assert d["roofline_ray"]["bound"] == "hbm" and 0.5 < d["roofline_ray"]["frac"] < 1.0
