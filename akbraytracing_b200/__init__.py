@@ -6,9 +6,10 @@ from .wavecalc import (PHASE_EXACT, PHASE_FAITHFUL, PHASE_REFERENCED, WaveField3
                        forward_propagation_cupy_batch_multi_gpu, forward_propagation_numpy_batch,
                        fresnel_sum, fresnel_sum_sharded)
 from .raytrace import (PlanePoints, ell, intersect_reflect, mirr_ray_intersection, norm_vector,
-                       normalize_vector, plane_ray_intersection, reflect_ray, trace_chain, trace_chain_batched)
+                       normalize_vector, plane_ray_intersection, reflect_ray, rotation_matrices, trace_chain,
+                       trace_chain_batched, wavefront_opl)
 from .handoff import calc_dS, opl_to_field
 from .psf import compute_psf_fft, field_to_pupil, psf_to_db
-from .stagechain import load_handoff, parse_conditions, run_stage_chain, write_handoff
+from .stagechain import auto_phase_mode, load_handoff, parse_conditions, run_stage_chain, write_handoff
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -30,8 +30,15 @@ SIGNATURES = {
     "akb_last_error": (ctypes.c_char_p, []),
     "akb_version": (_c_int, []),
     "akb_device_count": (_c_int, []),
+    "akb_trim": (_c_int, [_c_int]),
     "akb_fresnel_sum": (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_dbl, _vp, _c_int, _vp]),
     "akb_fresnel_sum_host": (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_dbl, _vp, _c_int, _c_int]),
+    "akb_fresnel_sum_sharded": (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_dbl, _vp,
+                                          _c_int, _c_int, _vp]),
+    "akb_allgather_blocks": (_c_int, [_vp, _c_int, _c_int, _vp, _c_i64, _c_int, _vp]),
+    "akb_nccl_unique_id": (_c_int, [_vp]),
+    "akb_nccl_comm_init": (_c_int, [ctypes.POINTER(_vp), _c_int, _c_int, _vp]),
+    "akb_nccl_comm_destroy": (_c_int, [_vp]),
     "akb_shard_range": (_c_int, [_c_i64, _c_int, _c_int, ctypes.POINTER(_c_i64), ctypes.POINTER(_c_i64)]),
     "akb_launch_count": (_c_i64, [_c_int]),
     "akb_fresnel_variant_name": (ctypes.c_char_p, []),
@@ -45,10 +52,11 @@ SIGNATURES = {
     "akb_normalize_vector": (_c_int, [_vp, _c_i64, _vp, _c_uint, _vp, _vp]),
     "akb_plane_ray_intersection": (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp]),
     "akb_intersect_reflect": (_c_int, [_vp, _vp, _vp, _c_i64, _c_int, _vp, _vp, _vp, _c_uint, _vp, _vp]),
-    "akb_trace_chain": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _c_uint, _vp, _vp]),
+    "akb_trace_chain": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_uint, _vp, _vp]),
+    "akb_wavefront_opl": (_c_int, [_vp, _vp, _vp, _c_int, _c_i64, _vp, _vp, _vp, _c_dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "akb_trace_chain_batched": (_c_int, [_vp, _vp, _c_int, _vp, _c_int, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),
     "akb_intersect_reflect_host":(_c_int, [_vp, _vp, _vp, _c_i64, _c_int, _vp, _vp, _vp, _vp, _c_int]),
-    "akb_trace_chain_host": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int]),
+    "akb_trace_chain_host": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int]),
     "akb_calc_ds": (_c_int, [_vp, _c_i64, _c_i64, _vp, _vp]),
     "akb_opl_to_field": (_c_int, [_vp, _vp, _c_i64, _c_dbl, _vp, _vp]),
     "akb_fp64_peak_probe": (_c_int, [_c_int, ctypes.POINTER(_c_dbl), _vp]),
@@ -118,6 +126,17 @@ def is_torch(x) -> bool:
     return mod == "torch" or mod.startswith("torch.")
 
 
+def is_cuda_array(x) -> bool:
+    """A non-torch object exposing __cuda_array_interface__ (CuPy / Numba device arrays)."""
+    return (not is_torch(x)) and hasattr(x, "__cuda_array_interface__")
+
+
+def from_cuda_array(x):
+    """Zero-copy torch view of a __cuda_array_interface__ object (same pointer, device taken from it)."""
+    import torch
+    return torch.as_tensor(x, device="cuda")
+
+
 def torch_stream_ptr(device):
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
@@ -130,6 +149,8 @@ def dev_ptr(t):
 def dev_f64(t, device=None):
     """A contiguous float64 CUDA tensor (no copy when it already is one)."""
     import torch
+    if is_cuda_array(t):
+        t = from_cuda_array(t)
     if not is_torch(t):
         t = torch.as_tensor(np.ascontiguousarray(t, dtype=np.float64))
     if device is None:
@@ -139,6 +160,8 @@ def dev_f64(t, device=None):
 
 def dev_c128(t, device=None):
     import torch
+    if is_cuda_array(t):
+        t = from_cuda_array(t)
     if not is_torch(t):
         t = torch.as_tensor(np.ascontiguousarray(t, dtype=np.complex128))
     if device is None:

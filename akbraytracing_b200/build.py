@@ -14,7 +14,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libakb_b200.so")
-SOURCES = ["common.cu", "fresnel.cu", "ray.cu", "handoff.cu", "probe.cu"]
+SOURCES = ["common.cu", "fresnel.cu", "sharded.cu", "ray.cu", "handoff.cu", "probe.cu"]
 HEADERS = [os.path.join(CSRC, "akb_common.cuh"), os.path.join(os.path.dirname(PKG), "include", "akb_b200.h")]
 
 NVCC_FLAGS = [
@@ -45,13 +45,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = _nvcc()
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("AKB_AB_VARIANTS") == "1":  # extra pair-kernel variants for tools/variant_bench.py
+        flags.append("-DAKB_AB_VARIANTS")
     objs = []
     build_dir = os.path.join(PKG, "build")
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
@@ -64,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
     link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
-            "-Xcompiler", "-fPIC", "-o", LIB, *objs]
+            "-Xcompiler", "-fPIC", "-o", LIB, *objs, "-ldl"]
     subprocess.run(link, check=True)
     return LIB
 

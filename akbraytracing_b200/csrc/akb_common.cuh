@@ -16,6 +16,32 @@ void tune_pool(int device);
 // cached non-blocking stream of the calling host thread on `device` (nullptr on failure)
 cudaStream_t host_stream(int device);
 
+// The "_host" entry points run on `device` but leave the caller's current device as they found it
+// (a co-resident PyTorch / CuPy keeps its own notion of the current device).
+struct DeviceScope {
+    int prev = -1;
+    bool changed = false;
+    // device < 0: stay on the current device.  Returns the device in use, or < 0 on error (akb_last_error set).
+    int enter(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            set_error("cudaGetDevice failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return -1;
+        }
+        if (device < 0 || device == prev) return prev;
+        if (cudaSetDevice(device) != cudaSuccess) {
+            set_error("cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(cudaGetLastError()));
+            return -1;
+        }
+        changed = true;
+        return device;
+    }
+    ~DeviceScope()
+    {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+
 #define AKB_CUDA(expr)                                                                         \
     do {                                                                                       \
         cudaError_t _e = (expr);                                                               \

@@ -42,7 +42,11 @@ void tune_pool(int device)
     if (device < 0 || device >= 64 || g_pool_tuned[device]) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX; // scratch stays cached in the pool between calls
+        // Scratch (packed tiles, partial sums <= 2 GiB, host-API slabs) stays cached in the device's default
+        // stream-ordered pool between calls, up to 4 GiB; anything above goes back to the driver at the next
+        // synchronisation, and akb_trim() hands back all of it (the pool is shared with nobody inside this
+        // library, but it is the process-wide default pool: a co-resident framework may want the memory).
+        uint64_t keep = 4ull << 30;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     g_pool_tuned[device] = true;
@@ -64,7 +68,19 @@ cudaStream_t host_stream(int device)
 
 extern "C" const char *akb_last_error(void) { return akb::g_error; }
 
-extern "C" int akb_version(void) { return 100; } // 0.1.0
+extern "C" int akb_version(void) { return 200; } // 0.2.0
+
+extern "C" int akb_trim(int device)
+{
+    akb::DeviceScope scope;
+    device = scope.enter(device);
+    if (device < 0) return AKB_ERR_CUDA;
+    cudaMemPool_t pool;
+    AKB_CUDA(cudaDeviceSynchronize());
+    AKB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    AKB_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return AKB_OK;
+}
 
 extern "C" int akb_device_count(void)
 {

@@ -41,9 +41,15 @@ constexpr int HEAD = 4; // per-tile header after the rows: reference point c_T (
 //                 table step go into the rounding constant (MAGIC - m_j, i.e. into the table index, free),
 //                 the remainder is added to f (one DADD); the complex multiply-accumulate with w_j
 //                 (4 DFMA) becomes a real one (2 DFMA).
-enum { FORM_TAN = 1, FORM_SHORTCOS = 2, FORM_POLAR = 4 };
-// rows of a packed source tile: sx, sy, sz, then (w_re, w_im) or (|w|, -frac(arg w), MAGIC - m)
-__host__ __device__ constexpr int rows_of(int form) { return (form & FORM_POLAR) ? 6 : 5; }
+//   FORM_WFOLD    (with FORM_TAN | FORM_POLAR | FORM_SHORTCOS) the weight rides in the cosine polynomial and the
+//                 amplitude in the accumulation:  W = h (|w| - |w|/2 f^2)  (one DFMA with the per-source
+//                 constants |w| and -|w|/2, one DMUL),  a = C - S tan f,  b = S + C tan f  (two DFMA on the
+//                 raw table entry),  acc += W (a, -b)  (two DFMA): 9 instead of 11 FP64 instructions for
+//                 polynomials + rotation + accumulation -- the table entry is never scaled component-wise.
+enum { FORM_TAN = 1, FORM_SHORTCOS = 2, FORM_POLAR = 4, FORM_WFOLD = 8 };
+// rows of a packed source tile: sx, sy, sz, then (w_re, w_im) or (|w|, -frac(arg w), MAGIC - m [, -|w|/2])
+__host__ __device__ constexpr int rows_of(int form) { return (form & FORM_WFOLD) ? 7 : (form & FORM_POLAR) ? 6 : 5; }
+constexpr int MAX_ROWS = 7;
 
 struct PhaseConst {
     double k;        // FAITHFUL: phase = fl(k * r)
@@ -53,16 +59,16 @@ struct PhaseConst {
     double u;        // EXACT: remainder in units -> radians
     double q_hi;     // EXACT: units per metre, k/u = q_hi + q_lo
     double q_lo;
+    double im_sign;  // -1 for k < 0: exp(+i|k|r) = conj(exp(-i|k|r)), evaluated with conjugated weights
 };
 
 // ---------------------------------------------------------------- pack
 __global__ void pack_sources_kernel(const double *__restrict__ sx, const double *__restrict__ sy,
                                     const double *__restrict__ sz, const double *__restrict__ u,
                                     const double *__restrict__ ds, long long N, long long padded, int tile,
-                                    int relative, int polar, double inv_u, double neg_u_hi, double neg_u_lo,
+                                    int relative, int polar, int ROWS, double im_sign, double inv_u, double neg_u_hi, double neg_u_lo,
                                     double *__restrict__ packed)
 {
-    const int ROWS = polar ? 6 : 5;
     long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= padded) return;
     long long jj = j < N ? j : N - 1; // padding repeats the last point (finite r) with zero weight
@@ -72,7 +78,7 @@ __global__ void pack_sources_kernel(const double *__restrict__ sx, const double 
         // u*ds exactly as NumPy's complex*real (CPU0402:102); the factor 2 (exact) pairs with
         // the 1/(2r) that the in-kernel square root produces for free.
         wr = mul(2.0, mul(u[2 * j], d));
-        wi = mul(2.0, mul(u[2 * j + 1], d));
+        wi = mul(im_sign, mul(2.0, mul(u[2 * j + 1], d)));
     }
     long long t_idx = j / tile;
     int o = (int)(j % tile);
@@ -94,6 +100,7 @@ __global__ void pack_sources_kernel(const double *__restrict__ sx, const double 
         t[3 * tile + o] = mag;
         t[4 * tile + o] = -g;
         t[5 * tile + o] = sub(AKB_RND_MAGIC, m);
+        if (ROWS > 6) t[6 * tile + o] = mul(mag, -0.5); // FORM_WFOLD: the f^2 coefficient of |w| cos f
     } else {
         t[3 * tile + o] = wr;
         t[4 * tile + o] = wi;
@@ -172,18 +179,25 @@ struct PairA {
 
 // ---- REFERENCED mode: optical path relative to a per-tile reference point -------------------------
 // r_ij is never formed as one double (its rounding alone is k*ulp(r)/2 = 7e-5 rad at 146 m, 1.35 nm).
-// For detector point d and the reference point c of a source tile,  D = d - c  and  r_ref = |D|  are
-// evaluated once per (detector, tile) in double-double; for a source s_j = c + e_j of the tile
-//     r_ij^2 - r_ref^2 = sum_c e_c (e_c - 2 D_c) =: ds          (small numbers, full relative precision)
-//     r_ij   - r_ref   = ds / (sqrt(r_ref^2 + ds) + r_ref)      (one correctly rounded quotient)
-// so the path difference carries 1 ulp of ITSELF (<= 2e-18 m for a 15 mm tile), and the phase is
-// (k r_ref mod 2 pi, held per (detector, tile) with ~1e-10 rad) + k (r_ij - r_ref) reduced exactly.
+// For detector point d and the reference point c of a source tile,  D = d - c,  S = |D|^2 (double-double, high
+// word S, low word folded into the reference phase) and  R = RN(sqrt(S))  are evaluated once per
+// (detector, tile); for a source s_j = c + e_j of the tile
+//     ds  = r_ij^2 - |D|^2 = sum_c e_c (e_c - 2 D_c)            (small numbers, full relative precision)
+//     rho = sqrt(S + ds)  by one Goldschmidt step from MUFU.RSQ64H:  g1 ~ rho (2^-41),  h1 ~ 1/(2 rho)
+//     r_ij - R = (g1 - R) + (S - g1^2 + ds) h1                   (the Newton residual of rho, evaluated AROUND R:
+//                                                                 g1 - R is exact, S - g1^2 + ds loses nothing)
+// so the path difference carries 1 ulp of ITSELF (<= 2e-18 m for a 15 mm tile) without any division, at the cost
+// of the plain square root (11 FP64 instructions for ds -> (r - R, 1/(2r)); the quotient form ds/(rho + R) of
+// round 1 took 15).  The phase of a pair is  k R (mod 2 pi, per (detector, tile))  +  k (r_ij - R)  reduced
+// exactly.  The first part is NOT added per pair: the accumulator of a detector point lives in the phase frame
+// of the current tile and is rotated by exp(-i k (R_prev - R_new)) when the tile changes (a complex multiply per
+// (detector, tile)), and by exp(-i k R_last) before it is stored.
 struct RefCtx {
     double gx, gy, gz; // -2 D (high words)
-    double s_ref;      // |D|^2 (high word)
-    double r_ref;      // |D|   (high word)
-    double phi;        // frac(k r_ref / u) in [-1/2, 1/2], from the double-double value
-    int n_ref;         // rint(k r_ref / u) mod 2^32
+    double s_ref;      // S: |D|^2 (high word)
+    double r_ref;      // R = RN(sqrt(S))
+    double phi;        // frac(k (R + low word correction) / u) in [-1/2, 1/2]
+    int n_ref;         // rint(k R / u) mod 2^32
 };
 
 __device__ __forceinline__ void two_sum(double a, double b, double &s, double &e)
@@ -216,10 +230,13 @@ __device__ __forceinline__ RefCtx make_ref_ctx(double X, double Y, double Z, dou
     r.gy = -2.0 * dh[1];
     r.gz = -2.0 * dh[2];
     r.s_ref = sh;
-    double r0 = __dsqrt_rn(sh), rl = 0.0;
-    if (r0 > 0.0) rl = __ddiv_rn(fma_(-r0, r0, sh) + sl, 2.0 * r0); // sqrt(sh + sl) = r0 + rl
+    const double r0 = __dsqrt_rn(sh);
+    // the pairs measure their distance from R = r0 itself (not from sqrt(sh)); what the reference phase still
+    // owes is the low word of |D|^2:  sqrt(sh + sl + ds) = sqrt(sh + ds) + sl / (2 r)  (r ~ r0 here)
+    double rl = 0.0;
+    if (r0 > 0.0) rl = __ddiv_rn(sl, 2.0 * r0);
     r.r_ref = r0;
-    // k r_ref / u = n_ref + phi with (r0 + rl) * (q_hi + q_lo)
+    // k R / u = n_ref + phi with (r0 + rl) * (q_hi + q_lo)
     const double t0 = fma_(r0, pc.q_hi, magic);
     const double n0 = add(t0, KC[KC_NEG_MAGIC]);
     double phi = fma_(r0, pc.q_hi, -n0);
@@ -230,33 +247,42 @@ __device__ __forceinline__ RefCtx make_ref_ctx(double X, double Y, double Z, dou
     return r;
 }
 
-// MUFU.RCP64H + 2 Newton steps: 1/b to < 1 ulp
-__device__ __forceinline__ double rcp_refined(double b)
+// acc <- acc * exp(-i (m u + dphi u)):  m whole table steps (any int: the table is periodic in 2^32) and a
+// fraction |dphi| <= 1.  `sg` = +1 when the imaginary accumulator holds -Im (FORM_WFOLD), -1 when it holds +Im.
+template <int TBL>
+__device__ __forceinline__ void rotate_acc(double &ar, double &ai, const double2 *table, int m, double dphi,
+                                           const PhaseConst &pc, double sg)
 {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
-    double e = fma_(-b, y, 1.0);
-    y = fma_(y, e, y);
-    e = fma_(-b, y, 1.0);
-    return fma_(y, e, y);
+    const double2 cs = table[m & (TBL - 1)];
+    const double x = mul(dphi, pc.u); // |x| <= 2 pi / TBL
+    const double z = mul(x, x);
+    const double c = fma_(z, fma_(z, 1.0 / 24.0, -0.5), 1.0);                    // next term x^6/720 <= 2e-20
+    const double sn = mul(x, fma_(z, fma_(z, 1.0 / 120.0, -1.0 / 6.0), 1.0));    // next term x^7/5040
+    const double cr = fma_(-cs.y, sn, mul(cs.x, c));                             // cos(m u + x)
+    const double sr = mul(sg, fma_(cs.x, sn, mul(cs.y, c)));                     // sin(m u + x), signed for the storage form
+    const double nr = fma_(-ai, sr, mul(ar, cr));
+    ai = fma_(ar, sr, mul(ai, cr));
+    ar = nr;
 }
 
-// phase A of a REFERENCED pair from ds = r^2 - r_ref^2
+// phase A of a REFERENCED pair from ds = r^2 - |D|^2
 __device__ __forceinline__ PairA pair_phase_a_ref_from_ds(const RefCtx &rc, double ds, const PhaseConst &pc, double magic)
 {
     const double s = add(rc.s_ref, ds);
+    const double y = rsqrt_approx(s);
+    const double g = mul(s, y);
+    const double h0 = __hiloint2double(__double2hiint(y) - 0x00100000, 0); // y/2, exact (akb_common.cuh)
+    const double e = fma_(-g, h0, 0.5);
+    const double g1 = fma_(g, e, g);
     PairA a;
-    double rho;
-    sqrt_and_half_rinv(s, rho, a.h);
-    const double den = add(rho, rc.r_ref);
-    const double y = rcp_refined(den);
-    const double q = mul(ds, y);
-    a.p = fma_(fma_(-den, q, ds), y, q);                     // r - r_ref, correctly rounded quotient
-    a.t = add(fma_(a.p, pc.q_hi, rc.phi), magic);            // MAGIC + rint((k (r - r_ref))/u + phi)
+    a.h = fma_(h0, e, h0);
+    const double d = add(fma_(-g1, g1, rc.s_ref), ds);  // S + ds - g1^2: the first part is -ds to within 2^-41, the sum exact
+    a.p = fma_(d, a.h, sub(g1, rc.r_ref));              // r - R
+    a.t = fma_(a.p, pc.q_hi, magic);                    // MAGIC - m_j + rint(k (r - R)/u)
     return a;
 }
 
-// (ex, ey, ez) = source - tile reference; r^2 - r_ref^2 = sum_c e_c (e_c - 2 D_c)
+// (ex, ey, ez) = source - tile reference; r^2 - |D|^2 = sum_c e_c (e_c - 2 D_c)
 __device__ __forceinline__ PairA pair_phase_a_ref(const RefCtx &rc, double ex, double ey, double ez,
                                                   const PhaseConst &pc, double magic)
 {
@@ -331,11 +357,18 @@ __device__ __forceinline__ double2 table_entry(const double2 *table, int q)
 //
 // FORM_POLAR: `magic_j` = MAGIC - m_j is the rounding constant a.t was formed with and `g_j` the
 // (negated) remainder of the source's weight phase; |f| then reaches pi/TBL * 2.
+//
+// FORM_WFOLD: `w_j` = |w_j| and `nhw_j` = -|w_j|/2 enter the cosine polynomial, so cf comes back as
+// W = h |w_j| cos f, the factor of the whole pair.
 template <int MODE, int TBL, int FORM>
-__device__ __forceinline__ void pair_phase_b(const PairA &a, const PhaseConst &pc, double t2, double phi,
-                                             double magic_j, double g_j, double &cf, double &sf)
+__device__ __forceinline__ void pair_phase_b(const PairA &a, const PhaseConst &pc, double t2,
+                                             double magic_j, double g_j, double w_j, double nhw_j, double &cf,
+                                             double &sf)
 {
     constexpr bool POLAR = (FORM & FORM_POLAR) != 0;
+    static_assert(!(FORM & FORM_WFOLD) || (FORM & (FORM_TAN | FORM_POLAR | FORM_SHORTCOS)) ==
+                                              (FORM_TAN | FORM_POLAR | FORM_SHORTCOS),
+                  "FORM_WFOLD builds on the tan / polar / short-cosine formulation");
     constexpr int STEPS = POLAR ? TBL / 2 : TBL; // |f| <= pi / STEPS
     const double n = POLAR ? sub(a.t, magic_j) : add(a.t, KC[KC_NEG_MAGIC]);
     double f;
@@ -345,14 +378,14 @@ __device__ __forceinline__ void pair_phase_b(const PairA &a, const PhaseConst &p
         if (POLAR) f = add(f, g_j);
     } else {
         f = fma_(a.p, pc.q_hi, -n); // exact: the difference fits in 53 bits
-        if (MODE == AKB_PHASE_REFERENCED) f = add(f, phi);
         f = fma_(a.p, pc.q_lo, f);
         f = POLAR ? fma_(f, pc.u, g_j) : mul(f, pc.u);
     }
     const double z = mul(f, f);
     static_assert(!(FORM & FORM_SHORTCOS) || STEPS >= 2048, "short cosine needs |f| <= pi/2048");
-    const double c1 = (FORM & FORM_SHORTCOS) ? fma_(z, -0.5, 1.0)                          // f^4/24 <= 2.3e-13
-                                             : fma_(z, fma_(KC[KC_TC1], z, -0.5), 1.0);    // cos f
+    const double c1 = (FORM & FORM_WFOLD)      ? fma_(z, nhw_j, w_j)                       // |w| (1 - f^2/2)
+                      : (FORM & FORM_SHORTCOS) ? fma_(z, -0.5, 1.0)                        // f^4/24 <= 2.3e-13
+                                               : fma_(z, fma_(KC[KC_TC1], z, -0.5), 1.0);  // cos f
     if (FORM & FORM_TAN) {
         double e1;
         if (STEPS >= 1024) {
@@ -479,17 +512,22 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
         constexpr bool ROW = decltype(row_tag)::value;
         int stage = 0;
         uint32_t parity = 0;
+        RefCtx rc[REF ? DPT : 1]; // REFERENCED: the phase frame (tile reference) the accumulators live in
+        constexpr double SG = (FORM & FORM_WFOLD) ? 1.0 : -1.0;
         for (int t = t0; t < t1; ++t) {
             mbar_wait(bars_s + 8 * stage, parity);
             double *T = tiles + stage * TILE_DOUBLES;
             const long long left = n_padded - (long long)t * TILE;
             const int cnt = left < TILE ? (int)left : TILE; // multiple of 2
-            RefCtx rc[REF ? DPT : 1];
-            if (REF) { // once per (detector point, tile): double-double distance to the tile's reference point
+            if (REF) { // once per (detector point, tile): double-double distance to the tile's reference point,
+                       // and the accumulated field moves from the previous tile's phase frame into this one
 #pragma unroll
-                for (int d = 0; d < DPT; ++d)
-                    rc[d] = make_ref_ctx(X[d], Y[d], Z[d], T[ROWS * TILE + 0], T[ROWS * TILE + 1], T[ROWS * TILE + 2], pc,
-                                         magic);
+                for (int d = 0; d < DPT; ++d) {
+                    const RefCtx nc = make_ref_ctx(X[d], Y[d], Z[d], T[ROWS * TILE + 0], T[ROWS * TILE + 1],
+                                                   T[ROWS * TILE + 2], pc, magic);
+                    if (t > t0) rotate_acc<TBL>(ar[d], ai[d], table, rc[d].n_ref - nc.n_ref, sub(rc[d].phi, nc.phi), pc, SG);
+                    rc[d] = nc;
+                }
             }
             if (ROW) { // the sx row becomes fl((x0 - sx)^2), CPU0402:76-77 (REFERENCED: e_x (e_x - 2 D_x))
                 for (int q = threadIdx.x; q < TILE; q += THREADS) {
@@ -504,7 +542,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
             for (int j = 0; j < cnt; j += SPI) {
                 // rows of the SPI sources of this iteration: x (ROW: dx^2), y, z, then (w_re, w_im) -- or,
                 // FORM_POLAR: (|w|, -frac(arg w), MAGIC - m)
-                double S[6][SPI];
+                double S[MAX_ROWS][SPI];
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) {
                     if (SPI == 2) {
@@ -533,7 +571,6 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                 double cf[NP], sf[NP];
 #pragma unroll
                 for (int d = 0; d < DPT; ++d) {
-                    const int n_ref = REF ? rc[d].n_ref : 0; // table index = n_ref + rint(k (r - r_ref)/u + phi)
 #pragma unroll
                     for (int q = 0; q < SPI; ++q) {
                         const int i = SPI * d + q;
@@ -546,16 +583,34 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                         } else {
                             a[i] = pair_phase_a<MODE>(X[d], Y[d], Z[d], S[0][q], S[1][q], S[2][q], pc, S[5][q]);
                         }
-                        cs[i] = table_entry<TBL>(table, __double2loint(a[i].t) + n_ref);
+                        cs[i] = table_entry<TBL>(table, __double2loint(a[i].t));
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < NP; ++i)
-                    pair_phase_b<MODE, TBL, FORM>(a[i], pc, t2, REF ? rc[i / SPI].phi : 0.0, S[5][i % SPI],
-                                                  S[4][i % SPI], cf[i], sf[i]);
+                    pair_phase_b<MODE, TBL, FORM>(a[i], pc, t2, S[5][i % SPI],
+                                                  S[4][i % SPI], S[3][i % SPI], S[6][i % SPI], cf[i], sf[i]);
                 // phase C: rotate by the table entry, then accumulate.  The accumulation is ordered by
                 // source and by operation so that consecutive DFMAs share their first operand (the weight
                 // of one source): served by the operand-reuse cache, they read 2 registers, not 3.
+                if constexpr ((FORM & FORM_WFOLD) != 0) {
+                    // cf = W = h |w_j| cos f, sf = tan f:  acc += W ((C - S tan f) - i (S + C tan f))
+                    // Two passes, so that the two DFMAs that share an operand (tan f, then W) are neighbours in
+                    // program order with their inputs long since ready: ptxas then keeps them adjacent and the
+                    // operand-reuse cache serves the shared operand (a DFMA reading three fresh registers
+                    // costs about two extra FP64-pipe cycles, tools/ubench/fp64_banks3.cu).
+                    double ca[NP], sb[NP];
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) {
+                        ca[i] = fma_(-cs[i].y, sf[i], cs[i].x);
+                        sb[i] = fma_(cs[i].x, sf[i], cs[i].y);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) {
+                        ar[i / SPI] = fma_(cf[i], ca[i], ar[i / SPI]);
+                        ai[i / SPI] = fma_(cf[i], sb[i], ai[i / SPI]); // -Im: the sign is applied at the store
+                    }
+                } else {
                 double c[NP], sn[NP];
 #pragma unroll
                 for (int i = 0; i < NP; ++i) {
@@ -583,6 +638,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                         for (int d = 0; d < DPT; ++d) ar[d] = fma_(wi, sn[SPI * d + q], ar[d]);
                     }
                 }
+                }
             }
             __syncthreads(); // every thread is done with this stage
             if (threadIdx.x == 0 && t + STAGES < t1) {
@@ -595,6 +651,10 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                 parity ^= 1;
             }
         }
+        if (REF && t1 > t0) { // out of the last tile's phase frame
+#pragma unroll
+            for (int d = 0; d < DPT; ++d) rotate_acc<TBL>(ar[d], ai[d], table, rc[d].n_ref, rc[d].phi, pc, SG);
+        }
     };
     if (row)
         run_tiles(std::true_type{});
@@ -605,7 +665,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
 #pragma unroll
     for (int d = 0; d < DPT; ++d) {
         long long i = base + d;
-        if (i < M) o[i] = make_double2(ar[d], ai[d]);
+        if (i < M) o[i] = make_double2(ar[d], mul((FORM & FORM_WFOLD) ? -pc.im_sign : pc.im_sign, ai[d]));
     }
 }
 
@@ -647,6 +707,8 @@ PhaseConst make_phase_const(double k, int table)
     // u = 2*pi/table: a power-of-two multiple of pi, exact in both words
     const double su = 2.0 / table, si = table / 2.0;
     PhaseConst pc;
+    pc.im_sign = k < 0.0 ? -1.0 : 1.0;
+    k = k < 0.0 ? -k : k;
     pc.k = k;
     pc.u = pi_hi * su;
     pc.inv_u = ipi_hi * si;
@@ -682,25 +744,34 @@ KernelEntry make_entry(const char *name)
 }
 
 // Kernel variants: <points per thread, tile, stages, table entries, min resident blocks/SM, formulation
-// [, sources per iteration, threads]>.  Entries 0, 1, 3 are used by the size-aware default choice;
-// AKB_FRESNEL_VARIANT=<n> forces one (tools/variant_bench.py).
+// [, sources per iteration, threads]>.  Entries 0..3 are the product: the size-aware default choice picks among
+// them.  Further entries exist only in A/B builds (AKB_AB_VARIANTS=1 python -m akbraytracing_b200.build);
+// AKB_FRESNEL_VARIANT=<n> forces one (tools/variant_bench.py) and an index that does not exist is an error.
+constexpr int FORM_DEFAULT = FORM_TAN | FORM_POLAR | FORM_SHORTCOS | FORM_WFOLD;
+enum { V_DEFAULT = 0, V_DPT2 = 1, V_DPT1 = 2, V_REFERENCED = 3 };
 const KernelEntry *kernel_table(int *count)
 {
     static const KernelEntry entries[] = {
-        // default: 31 FP64 instructions per pair, 122 registers, 2 x 256 threads per SM (measured best:
-        // 3 blocks/SM at 80 registers spill, 1 block/SM starves the FP64 pipe, block sizes that are not a
-        // multiple of 4 warps lose 10-20 %, one 640/768-thread block per SM sharing one table loses 2-4 %)
-        make_entry<4, 256, 3, 4096, 2, FORM_TAN | FORM_POLAR | FORM_SHORTCOS>(
-            "dpt4 tile256x3 table4096 tan polar shortcos 2 blocks/SM"),
+        // default: 25.5 FP64 instructions per pair on planar-row blocks (29 in the general loop), 2 x 256
+        // threads per SM (measured in round 1: 3 blocks/SM at 80 registers spill, 1 block/SM starves the FP64
+        // pipe, block sizes that are not a multiple of 4 warps lose 10-20 %, one 640/768-thread block per SM
+        // sharing one table loses 2-4 %)
+        make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT>("dpt4 tile256x3 table4096 tan polar shortcos wfold 2 blocks/SM"),
         // small problems: fewer points per thread, and a 2048-entry table (8 sincospi per thread and block)
         make_entry<2, 256, 3, 2048, 2, FORM_TAN | FORM_POLAR>("dpt2 tile256x3 table2048 tan polar"),
-        // the round-1 formulation (sin/cos polynomials, complex weights), kept for A/B runs
-        make_entry<4, 512, 2, 1024, 3, 0>("dpt4 tile512x2 table1024 sincos 3 blocks/SM"),
         make_entry<1, 128, 4, 2048, 2, FORM_TAN | FORM_POLAR>("dpt1 tile128x4 table2048 tan polar"),
-        make_entry<4, 512, 2, 2048, 2, FORM_TAN | FORM_POLAR>("dpt4 tile512x2 table2048 tan polar 2 blocks/SM"),
-        // REFERENCED keeps 7 more doubles per detector point in registers: 2 points per thread
-        make_entry<2, 256, 3, 4096, 2, FORM_TAN | FORM_POLAR | FORM_SHORTCOS>(
-            "dpt2 tile256x3 table4096 tan polar shortcos 2 blocks/SM"),
+        // REFERENCED keeps more state per detector point in registers: 2 points per thread
+        make_entry<2, 256, 3, 4096, 2, FORM_DEFAULT>("dpt2 tile256x3 table4096 tan polar shortcos wfold 2 blocks/SM"),
+#ifdef AKB_AB_VARIANTS
+        // 4: the round-1 default (scaled table entry, 27.5 / 31 instructions per pair)
+        make_entry<4, 256, 3, 4096, 2, FORM_TAN | FORM_POLAR | FORM_SHORTCOS>(
+            "dpt4 tile256x3 table4096 tan polar shortcos 2 blocks/SM"),
+        // 5: the first formulation (sin/cos polynomials, complex weights)
+        make_entry<4, 512, 2, 1024, 3, 0>("dpt4 tile512x2 table1024 sincos 3 blocks/SM"),
+        // 6, 7: one source per iteration; 2 points per thread with the default formulation
+        make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT, 1>("dpt4 spi1 tile256x3 table4096 wfold"),
+        make_entry<8, 256, 3, 4096, 1, FORM_DEFAULT, 1>("dpt8 spi1 tile256x3 table4096 wfold 1 block/SM"),
+#endif
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));
     return entries;
@@ -755,24 +826,34 @@ int resident_blocks(const KernelEntry &ke, int mode)
     return per_sm;
 }
 
+// AKB_FRESNEL_VARIANT: -2 = not set, >= 0 = forced entry, -3 = set to something that does not exist
+int forced_variant()
+{
+    static const int idx = [] {
+        const char *v = getenv("AKB_FRESNEL_VARIANT");
+        if (!v || !*v) return -2;
+        int n = 0;
+        kernel_table(&n);
+        char *end = nullptr;
+        const long want = strtol(v, &end, 10);
+        return (end && *end == 0 && want >= 0 && want < n) ? (int)want : -3;
+    }();
+    return idx;
+}
+
 const KernelEntry &selected_kernel(int mode, long long M = -1, long long N = -1, int sms = 148)
 {
     int n = 0;
     const KernelEntry *e = kernel_table(&n);
-    static int idx = -1; // -1: not read yet, -2: no override
-    if (idx == -1) {
-        const char *v = getenv("AKB_FRESNEL_VARIANT");
-        int want = v ? atoi(v) : -2;
-        idx = (want >= 0 && want < n) ? want : -2;
-    }
+    const int idx = forced_variant();
     if (idx >= 0) return e[idx];
-    int pick = mode == AKB_PHASE_REFERENCED ? 5 : 0;
+    int pick = mode == AKB_PHASE_REFERENCED ? V_REFERENCED : V_DEFAULT;
     // Small problems (C1: 64x64 detector points x 1e4 sources) cannot fill the SMs with 4 points per thread:
     // among the 4 / 2 / 1 points-per-thread variants take the one with the lowest estimated time,
     // FP64 instructions per pair / wave-fill efficiency of its best split plan.
     if (M > 0 && N > 0) {
-        const int order[3] = {pick, 1, 3};
-        const double instr[3] = {31.0, 32.0, 32.0};
+        const int order[3] = {pick, V_DPT2, V_DPT1};
+        const double instr[3] = {29.0, 32.0, 32.0};
         double best = 1e300;
         for (int o = 0; o < 3; ++o) {
             const KernelEntry &c = e[order[o]];
@@ -837,7 +918,9 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
         return AKB_OK;
     }
     AKB_REQUIRE(src_x && src_y && src_z && src_u, "source pointers must not be NULL");
-    AKB_REQUIRE(k >= 0.0 && k < 1.0e12, "wave number k must be in [0, 1e12) (k*r must stay below 3.4e12 rad: 2^51 table steps)");
+    AKB_REQUIRE(k > -1.0e12 && k < 1.0e12, "|k| must be below 1e12 (|k|*r must stay below 3.4e12 rad: 2^51 table steps)");
+    AKB_REQUIRE(forced_variant() != -3, "AKB_FRESNEL_VARIANT names a kernel variant this build does not have "
+                                        "(A/B variants need AKB_AB_VARIANTS=1 at build time)");
 
     int device = 0;
     AKB_CUDA(cudaGetDevice(&device));
@@ -884,7 +967,7 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     PhaseConst pc = make_phase_const(k, ke.table);
     pack_sources_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, st>>>(
         src_x, src_y, src_z, src_u, src_ds, N, padded, TILE, mode == AKB_PHASE_REFERENCED ? 1 : 0,
-        (ke.form & FORM_POLAR) ? 1 : 0, pc.inv_u, pc.neg_u_hi, pc.neg_u_lo, packed);
+        (ke.form & FORM_POLAR) ? 1 : 0, rows, pc.im_sign, pc.inv_u, pc.neg_u_hi, pc.neg_u_lo, packed);
     AKB_LAUNCH_CHECK();
 
     double *dst = splits > 1 ? partial : out;
@@ -956,8 +1039,9 @@ extern "C" int akb_fresnel_sum_host(const double *det_x, const double *det_y, co
     if (M == 0) return AKB_OK;
     AKB_REQUIRE(det_x && det_y && det_z && out, "detector/out pointers must not be NULL");
     AKB_REQUIRE(N == 0 || (src_x && src_y && src_z && src_u), "source pointers must not be NULL");
-    if (device >= 0) AKB_CUDA(cudaSetDevice(device)); // device < 0: the calling thread's current device
-    AKB_CUDA(cudaGetDevice(&device));
+    DeviceScope scope; // device < 0: the calling thread's current device; the caller's current device is restored on return
+    device = scope.enter(device);
+    if (device < 0) return AKB_ERR_CUDA;
     tune_pool(device);
     cudaStream_t st = host_stream(device);
     AKB_REQUIRE(st != nullptr, "could not create a stream on the device");

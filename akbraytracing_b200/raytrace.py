@@ -23,7 +23,8 @@ import numpy as np
 from . import _lib
 
 __all__ = ["mirr_ray_intersection", "norm_vector", "reflect_ray", "normalize_vector",
-           "plane_ray_intersection", "intersect_reflect", "trace_chain", "trace_chain_batched", "ell", "PlanePoints",
+           "plane_ray_intersection", "intersect_reflect", "trace_chain", "trace_chain_batched", "wavefront_opl",
+           "rotation_matrices", "ell", "PlanePoints",
            "Ell_define", "calcEll_Yvalue", "shift_x"]
 
 
@@ -37,11 +38,13 @@ def _coeffs(c) -> np.ndarray:
 
 
 class _Ctx:
-    """Device staging for one call: uploads NumPy inputs, allocates outputs, reads flags."""
+    """Device staging for one call: uploads NumPy inputs, allocates outputs, reads flags.
+    Device arrays = torch CUDA tensors or any object with __cuda_array_interface__ (used in place)."""
 
     def __init__(self, *arrays):
         import torch
         self.torch = torch
+        arrays = [_lib.from_cuda_array(a) if _lib.is_cuda_array(a) else a for a in arrays]
         self.numpy_io = not any(_lib.is_torch(a) for a in arrays)
         dev = None
         for a in arrays:
@@ -50,13 +53,35 @@ class _Ctx:
                 break
         self.device = dev if dev is not None else torch.device("cuda", torch.cuda.current_device())
         self.stream = _lib.torch_stream_ptr(self.device)
-        self.flags = torch.zeros(_lib.NFLAGS, dtype=torch.int32, device=self.device)
+        self._flags = None
+
+    @property
+    def flags(self):
+        """int32[NFLAGS] status block (the entry points zero it on the stream themselves)."""
+        if self._flags is None:
+            self._flags = self.torch.empty(_lib.NFLAGS, dtype=self.torch.int32, device=self.device)
+        return self._flags
 
     def rays(self, a):
         t = _lib.dev_f64(a, self.device)
         if t.dim() != 2 or t.shape[0] != 3:
             raise ValueError("ray arrays must have shape (3, N)")
         return t
+
+    def pair(self, a, b):
+        """Two (3, N) arrays of one call.  Like NumPy in the reference, a (3, 1) array broadcasts against
+        (3, N) (one launch point / one direction for every ray); any other mismatch is an error -- the kernels
+        index both arrays with the same N."""
+        ta, tb = self.rays(a), self.rays(b)
+        na, nb = ta.shape[1], tb.shape[1]
+        if na != nb:
+            if na == 1:
+                ta = ta.expand(3, nb).contiguous()
+            elif nb == 1:
+                tb = tb.expand(3, na).contiguous()
+            else:
+                raise ValueError(f"ray arrays have {na} and {nb} columns: they must match (or one of them be (3, 1))")
+        return ta, tb
 
     def empty(self, *shape):
         return self.torch.empty(*shape, dtype=self.torch.float64, device=self.device)
@@ -82,7 +107,7 @@ def _run(ctx, name, *args):
 def mirr_ray_intersection(coeffs, ray, source, negative=False):
     co = _coeffs(coeffs)
     ctx = _Ctx(ray, source)
-    r, s = ctx.rays(ray), ctx.rays(source)
+    r, s = ctx.pair(ray, source)
     p = ctx.empty(3, r.shape[1])
     _run(ctx, "akb_mirr_ray_intersection", _lib.host_ptr(co), _lib.dev_ptr(r), _lib.dev_ptr(s), r.shape[1],
          int(bool(negative)), _lib.dev_ptr(p), _lib.dev_ptr(ctx.flags), ctx.stream)
@@ -111,7 +136,7 @@ def norm_vector(coeffs, point):
 
 def reflect_ray(ray, N):
     ctx = _Ctx(ray, N)
-    r, n = ctx.rays(ray), ctx.rays(N)
+    r, n = ctx.pair(ray, N)
     return _normalising(ctx, "akb_reflect_ray", r.shape[1], (_lib.dev_ptr(r), _lib.dev_ptr(n)), ctx.empty(3, r.shape[1]))
 
 
@@ -124,7 +149,7 @@ def normalize_vector(vector):
 def plane_ray_intersection(coeffs, ray, source):
     co = _coeffs(coeffs)
     ctx = _Ctx(ray, source)
-    r, s = ctx.rays(ray), ctx.rays(source)
+    r, s = ctx.pair(ray, source)
     p = ctx.empty(3, r.shape[1])
     _run(ctx, "akb_plane_ray_intersection", _lib.host_ptr(co), _lib.dev_ptr(r), _lib.dev_ptr(s), r.shape[1],
          _lib.dev_ptr(p), ctx.stream)
@@ -139,7 +164,7 @@ def intersect_reflect(coeffs, ray, source, negative=False, want_normal=True, che
     synchronisation; misses then stay per-ray NaN, the mpmath flavour of III_I:296-301)."""
     co = _coeffs(coeffs)
     ctx = _Ctx(ray, source)
-    r, s = ctx.rays(ray), ctx.rays(source)
+    r, s = ctx.pair(ray, source)
     n = r.shape[1]
     p, rf = ctx.empty(3, n), ctx.empty(3, n)
     nv = ctx.empty(3, n) if want_normal else None
@@ -161,11 +186,14 @@ def intersect_reflect(coeffs, ray, source, negative=False, want_normal=True, che
 
 
 def trace_chain(coeffs_list, negative_list, plane_coeffs, ray, source, want_normals=False, want_reflects=False,
-                want_dist=True, check=True):
-    """K mirrors + detector plane + segment lengths in ONE kernel (BIG:2881-2905, BIG:11039-11054).
+                want_dist=True, check=True, want_opl=False):
+    """K mirrors + detector plane + segment lengths + optical path in ONE kernel (BIG:2881-2905, BIG:11039-11054,
+    BIG:3621-3623).
 
-    Returns dict(points (K,3,N), normals/reflects (K,3,N) or None, last_reflect (3,N),
-    det (3,N) or None, dist (K,N) or None, flags)."""
+    Returns dict(points (K,3,N), normals/reflects (K,3,N) or None, last_reflect (3,N), det (3,N) or None,
+    dist (K,N) or None, opl (N,) or None, flags).  ``opl`` = dist_0 + ... + dist_{K-1} (+ |det - P_K| with a
+    plane), the reference's totalDist.  ``check=False`` skips the flag read-back: no host synchronisation, misses
+    stay per-ray NaN (the mpmath flavour, III_I:296-301)."""
     K = len(coeffs_list)
     if not 1 <= K <= _lib.MAX_MIRRORS:
         raise ValueError(f"1..{_lib.MAX_MIRRORS} mirrors supported")
@@ -175,20 +203,32 @@ def trace_chain(coeffs_list, negative_list, plane_coeffs, ray, source, want_norm
         raise ValueError("negative_list must have one entry per mirror")
     plane = _coeffs(plane_coeffs) if plane_coeffs is not None else None
     ctx = _Ctx(ray, source)
-    r, s = ctx.rays(ray), ctx.rays(source)
+    r, s = ctx.pair(ray, source)
     n = r.shape[1]
-    pts = ctx.empty(K, 3, n)
-    nrm = ctx.empty(K, 3, n) if want_normals else None
-    rfl = ctx.empty(K, 3, n) if want_reflects else None
-    last = ctx.empty(3, n)
-    det = ctx.empty(3, n) if plane is not None else None
-    dist = ctx.empty(K, n) if want_dist else None
+    # one allocation for every output (rows of n doubles): points | normals | reflects | last | det | dist | opl | flags
+    rows = 3 * K + (3 * K if want_normals else 0) + (3 * K if want_reflects else 0) + 3 + (3 if plane is not None else 0) \
+        + (K if want_dist else 0) + (1 if want_opl else 0)
+    slab = ctx.empty(rows * n + 2)  # + 16 bytes: the int32[4] status block
+    at = [0]
+
+    def take(nrows, *shape):
+        v = slab[at[0] * n:(at[0] + nrows) * n].view(*shape)
+        at[0] += nrows
+        return v
+    pts = take(3 * K, K, 3, n)
+    nrm = take(3 * K, K, 3, n) if want_normals else None
+    rfl = take(3 * K, K, 3, n) if want_reflects else None
+    last = take(3, 3, n)
+    det = take(3, 3, n) if plane is not None else None
+    dist = take(K, K, n) if want_dist else None
+    opl = take(1, n) if want_opl else None
+    ctx._flags = slab[rows * n:].view(ctx.torch.int32)
     opt = lambda t: _lib.dev_ptr(t) if t is not None else None  # noqa: E731
     skip, flags = 0, [0] * _lib.NFLAGS
     for _ in range(2 * K + 1):
         _run(ctx, "akb_trace_chain", _lib.host_ptr(co), _lib.host_ptr(neg), K,
              _lib.host_ptr(plane) if plane is not None else None, _lib.dev_ptr(r), _lib.dev_ptr(s), n,
-             _lib.dev_ptr(pts), opt(nrm), opt(rfl), _lib.dev_ptr(last), opt(det), opt(dist), skip,
+             _lib.dev_ptr(pts), opt(nrm), opt(rfl), _lib.dev_ptr(last), opt(det), opt(dist), opt(opl), skip,
              _lib.dev_ptr(ctx.flags), ctx.stream)
         if not check:
             break
@@ -206,11 +246,65 @@ def trace_chain(coeffs_list, negative_list, plane_coeffs, ray, source, want_norm
             if t is not None:
                 t[first:] = nan
         last[:] = nan
-        if det is not None:
-            det[:] = nan
+        for t in (det, opl):
+            if t is not None:
+                t[:] = nan
     o = lambda t: ctx.out(t) if t is not None else None  # noqa: E731
     return dict(points=o(pts), normals=o(nrm), reflects=o(rfl), last_reflect=o(last), det=o(det), dist=o(dist),
-                flags=flags)
+                opl=o(opl), flags=flags)
+
+
+def rotation_matrices(theta_y, theta_z):
+    """R_y, R_z of rotate_vectors (BIG:917-931), built on the host with NumPy exactly like the reference."""
+    R_y = np.array([[np.cos(theta_y), 0, np.sin(theta_y)], [0, 1, 0], [-np.sin(theta_y), 0, np.cos(theta_y)]])
+    R_z = np.array([[np.cos(theta_z), -np.sin(theta_z), 0], [np.sin(theta_z), np.cos(theta_z), 0], [0, 0, 1]])
+    return R_y, R_z
+
+
+def wavefront_opl(last_point, last_dir, dist, plane_x, plane2_x=None, theta_y=None, theta_z=None, pivot=None,
+                  want_rotated=False):
+    """The tail of ``plot_result_debug(p, 'ray_wave')`` (BIG:3516-3558, 3611-3631) in one launch.
+
+    last_point, last_dir: (3,N) hit points / directions after the last mirror; dist: (K,N) segment lengths of
+    ``trace_chain`` (or None).  With ``theta_y, theta_z, pivot`` the bundle is first rotated into the detector frame
+    like the reference does (``rotate_vectors(v, theta_y, theta_z)`` / ``rotate_points(P, pivot, theta_y, theta_z)``).
+    Returns dict(det, opl[, det2, opl2][, point, dir]): detector points on x = plane_x (and x = plane2_x),
+    optical paths ``totalDist`` / ``totalDist2``."""
+    ctx = _Ctx(last_point, last_dir, dist)
+    p, v = ctx.pair(last_point, last_dir)
+    n = p.shape[1]
+    K = 0
+    d = None
+    if dist is not None:
+        d = _lib.dev_f64(dist, ctx.device)
+        if d.dim() != 2 or d.shape[1] != n:
+            raise ValueError("dist must have shape (K, N)")
+        K = d.shape[0]
+    rot = (theta_y is not None) or (theta_z is not None)
+    rz = ry = pv = None
+    if rot:
+        if pivot is None:
+            raise ValueError("a rotation needs the pivot point (focus_apprx)")
+        R_y, R_z = rotation_matrices(0.0 if theta_y is None else theta_y, 0.0 if theta_z is None else theta_z)
+        ry, rz = np.ascontiguousarray(R_y, dtype=np.float64), np.ascontiguousarray(R_z, dtype=np.float64)
+        pv = np.ascontiguousarray(np.asarray(pivot, dtype=np.float64).reshape(3))
+    det, opl = ctx.empty(3, n), ctx.empty(n)
+    det2 = ctx.empty(3, n) if plane2_x is not None else None
+    opl2 = ctx.empty(n) if plane2_x is not None else None
+    prot = ctx.empty(3, n) if want_rotated else None
+    vrot = ctx.empty(3, n) if want_rotated else None
+    import ctypes
+    px2 = ctypes.c_double(float(plane2_x)) if plane2_x is not None else None
+    opt = lambda t: _lib.dev_ptr(t) if t is not None else None  # noqa: E731
+    hp = lambda a: _lib.host_ptr(a) if a is not None else None  # noqa: E731
+    _run(ctx, "akb_wavefront_opl", _lib.dev_ptr(p), _lib.dev_ptr(v), opt(d), K, n, hp(rz), hp(ry), hp(pv),
+         float(plane_x), ctypes.byref(px2) if px2 is not None else None, opt(prot), opt(vrot), _lib.dev_ptr(det),
+         opt(det2), _lib.dev_ptr(opl), opt(opl2), ctx.stream)
+    o = lambda t: ctx.out(t) if t is not None else None  # noqa: E731
+    out = dict(det=o(det), opl=o(opl), det2=o(det2), opl2=o(opl2))
+    if want_rotated:
+        out.update(point=o(prot), dir=o(vrot))
+    return out
 
 
 def trace_chain_batched(coeffs_batch, negative_list, planes_batch, ray, source, want_det=True):
@@ -229,11 +323,11 @@ def trace_chain_batched(coeffs_batch, negative_list, planes_batch, ray, source, 
     if neg.shape[0] != K:
         raise ValueError("negative_list must have one entry per mirror")
     ctx = _Ctx(ray, source)
-    r, s = ctx.rays(ray), ctx.rays(source)
+    r, s = ctx.pair(ray, source)
     n = r.shape[1]
     det = ctx.empty(B, 3, n)
     stats = ctx.empty(B, 4)
-    miss = ctx.torch.zeros(B, dtype=ctx.torch.int32, device=ctx.device)
+    miss = ctx.torch.empty(B, dtype=ctx.torch.int32, device=ctx.device)  # zeroed by the entry point
     _run(ctx, "akb_trace_chain_batched", _lib.host_ptr(co), _lib.host_ptr(neg), K, _lib.host_ptr(planes), B,
          _lib.dev_ptr(r), _lib.dev_ptr(s), n, _lib.dev_ptr(det), _lib.dev_ptr(stats), _lib.dev_ptr(miss), ctx.stream)
     bad = miss > 0

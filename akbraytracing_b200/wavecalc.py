@@ -8,11 +8,16 @@ Mirrors (same names, positional order, return shapes/dtypes):
 * ``WaveField3D``                              CPU0402:17-52 / GPU0402:14-62
 
 Array kinds: NumPy in -> NumPy out (host buffers, H2D/D2H inside the call, like the CPU script);
-torch CUDA tensors in -> torch CUDA tensor out (zero copy, asynchronous on the current stream,
-like the CuPy scripts).  There is no CPU fallback.
+device arrays in -> torch CUDA tensor out (zero copy, asynchronous on torch's current stream, like
+the CuPy scripts).  A device array is a torch CUDA tensor or ANY object with ``__cuda_array_interface__``
+(the cp.ndarrays GPU0402:36-38 holds, Numba device arrays): its pointer is used in place, and the
+returned torch tensor exposes the same interface, so ``cp.asarray(result)`` is free.  Work is ordered
+on torch's current stream -- the legacy default stream unless the caller changed it, which is also
+CuPy's default, so a CuPy caller's pending kernels are ordered before ours.  There is no CPU fallback.
 """
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -25,8 +30,10 @@ __all__ = ["WaveField3D", "forward_propagation_numpy_batch", "forward_propagatio
            "PHASE_FAITHFUL", "PHASE_EXACT", "PHASE_REFERENCED"]
 
 
-def _any_torch(*arrays) -> bool:
-    return any(_lib.is_torch(a) for a in arrays)
+def _any_device(*arrays) -> bool:
+    """True when any argument is a device-side array: a torch tensor or any object exposing
+    ``__cuda_array_interface__`` (CuPy arrays, Numba device arrays: GPU0402:36-38 holds cp.ndarrays)."""
+    return any(_lib.is_torch(a) or _lib.is_cuda_array(a) for a in arrays)
 
 
 def _fresnel_host(x, y, z, sx, sy, sz, u, k, ds, mode, device=-1) -> np.ndarray:
@@ -55,6 +62,8 @@ def _fresnel_device(x, y, z, sx, sy, sz, u, k, ds, mode, device=None):
     import torch
     if device is None:
         for a in (x, y, z, sx, u):
+            if _lib.is_cuda_array(a):
+                a = _lib.from_cuda_array(a)
             if _lib.is_torch(a) and a.is_cuda:
                 device = a.device
                 break
@@ -87,7 +96,7 @@ def _fresnel_device(x, y, z, sx, sy, sz, u, k, ds, mode, device=None):
 
 def fresnel_sum(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds=None, mode=PHASE_FAITHFUL, device=None):
     """u_i = sum_j (u_j ds_j) exp(-1j k r_ij)/r_ij on one B200 (CPU0402:71-85 + :102)."""
-    if _any_torch(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, ds):
+    if _any_device(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, ds):
         return _fresnel_device(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, mode, device)
     return _fresnel_host(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, mode, -1 if device is None else device)
 
@@ -106,29 +115,22 @@ def forward_propagation_cupy_batch(x, y, z, u_back_x, u_back_y, u_back_z, u_back
 
 # ---------------------------------------------------------------- multi-GPU (detector sharding)
 
-def fresnel_sum_sharded(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds=None, mode=PHASE_FAITHFUL,
-                        group=None, compute=None, gather=True):
-    """One process per GPU: rank r computes the r-th ``array_split`` block of detector points
-    (GPU0402:77-79) against the full source set and the blocks are all-gathered (the NCCL
-    replacement of ``cp.concatenate``, GPU0402:135).  Every rank returns the full field.
+def _split(total, parts, rank):
+    """array_split block of `rank`: (begin, count) -- np.array_split / cp.array_split (GPU0402:77-79)."""
+    base, extra = divmod(int(total), int(parts))
+    return rank * base + min(rank, extra), base + (1 if rank < extra else 0)
 
-    ``compute`` exists for CPU tests of this host logic (gloo): it replaces the CUDA call.
-    """
+
+def _gather_blocks(local, total, group):
+    """All-gather of array_split blocks through torch.distributed on whatever device `local` lives on
+    (equal-size collective: every block is padded to the largest).  Used where NCCL cannot carry the
+    exchange (gloo groups); the NCCL path gathers in place inside akb_fresnel_sum_sharded."""
     import torch
     import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()):
-        raise RuntimeError("fresnel_sum_sharded needs an initialised torch.distributed process group")
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    total = int(x.shape[0])
-    begin, count = _lib.shard_range(total, world, rank) if compute is None else _split(total, world, rank)
-    sl = slice(begin, begin + count)
-    fn = compute if compute is not None else (lambda *a: fresnel_sum(*a, mode=mode))
-    local = fn(x[sl], y[sl], z[sl], u_back_x, u_back_y, u_back_z, u_back_u, k, ds)
-    if not gather:
-        return local
+    world = dist.get_world_size(group)
     if not _lib.is_torch(local):
         local = torch.as_tensor(np.ascontiguousarray(local))
-    # equal-size all-gather: pad every block to the largest (first total%world blocks hold +1)
+    count = int(local.shape[0])
     width = -(-total // world) if total else 0
     send = torch.zeros(width, dtype=local.dtype, device=local.device)
     send[:count] = local
@@ -136,38 +138,141 @@ def fresnel_sum_sharded(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds=N
     if width:
         dist.all_gather_into_tensor(recv.view(torch.float64) if recv.is_cuda else recv,
                                     send.view(torch.float64) if send.is_cuda else send, group=group)
-    pieces = []
-    for r in range(world):
-        _, c = _split(total, world, r)
-        pieces.append(recv[r * width:r * width + c])
+    pieces = [recv[r * width:r * width + _split(total, world, r)[1]] for r in range(world)]
     return torch.cat(pieces) if pieces else recv
 
 
-def _split(total, parts, rank):
-    base, extra = divmod(int(total), int(parts))
-    return rank * base + min(rank, extra), base + (1 if rank < extra else 0)
+def _sharded_over_group(compute_local, x, y, z, rest, group, gather):
+    """Host logic of the torch.distributed form: this rank's array_split block of the detector points goes to
+    `compute_local`, the blocks are gathered with _gather_blocks.  (tests/test_sharded_gloo.py drives this
+    with a CPU stand-in for `compute_local`; the product passes the CUDA call.)"""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    total = int(x.shape[0])
+    begin, count = _split(total, world, rank)
+    sl = slice(begin, begin + count)
+    local = compute_local(x[sl], y[sl], z[sl], *rest)
+    return _gather_blocks(local, total, group) if gather else local
 
 
-def forward_propagation_cupy_batch_multi_gpu(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, devices=None):
+_own_comms = {}  # id(group) -> ncclComm_t made by akb_nccl_comm_init (when PyTorch's cannot be borrowed)
+
+
+def _nccl_comm(group, device):
+    """An ncclComm_t spanning `group` on this rank's device: PyTorch's own communicator when the group runs on
+    NCCL (ProcessGroupNCCL._comm_ptr), else one created through the C-ABI from a unique id that rank 0
+    hands out over the group."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    key = id(group) if group is not None else 0
+    if key in _own_comms:
+        return _own_comms[key]
+    pg = group if group is not None else dist.group.WORLD
+    try:
+        if os.environ.get("AKB_OWN_NCCL_COMM") == "1":
+            raise RuntimeError("own communicator requested")
+        backend = pg._get_backend(torch.device(device))
+        if hasattr(backend, "_comm_ptr"):
+            ptr = int(backend._comm_ptr())
+            if ptr:
+                return ptr
+    except Exception:  # noqa: BLE001 -- not an NCCL group, or a PyTorch without _comm_ptr: make our own
+        pass
+    L = _lib.load()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    uid = ctypes.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(L.akb_nccl_unique_id(uid), "akb_nccl_unique_id")
+    box = [uid.raw]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(pg, 0) if group is not None else 0, group=group)
+    uid = ctypes.create_string_buffer(box[0], 128)
+    comm = ctypes.c_void_p()
+    with torch.cuda.device(device):
+        _lib.check(L.akb_nccl_comm_init(ctypes.byref(comm), world, rank, uid), "akb_nccl_comm_init")
+    _own_comms[key] = comm.value
+    return comm.value
+
+
+def fresnel_sum_sharded(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds=None, mode=PHASE_FAITHFUL,
+                        group=None, gather=True, device=None, broadcast_sources=False):
+    """One process per GPU (GPU0402_multi.py:123-229 with processes instead of host threads): rank r computes the
+    r-th ``array_split`` block of the detector points (GPU0402:77-79) against the full source set and the blocks are
+    all-gathered (the NCCL replacement of ``cp.concatenate``, GPU0402:135).  Every rank passes the same full
+    arrays and every rank returns the full field -- NumPy in, NumPy out; device arrays in, a torch CUDA tensor out.
+
+    On an NCCL-capable group the whole call is ``akb_fresnel_sum_sharded`` (block kernel + in-place NCCL
+    all-gather on the current stream).  On a group that cannot move device memory (gloo) the block is
+    computed on this rank's GPU and gathered through the group.  ``gather=False`` returns the local block only.
+    ``broadcast_sources``: take the source arrays from rank 0 (the reference keeps them on device 0)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("fresnel_sum_sharded needs an initialised torch.distributed process group")
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    arrays = (x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, ds)
+    was_numpy = not _any_device(*arrays)
+    if device is None:
+        device = next((a.device for a in arrays if _lib.is_torch(a) and a.is_cuda), None)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    total = int(x.shape[0])
+    rest = (u_back_x, u_back_y, u_back_z, u_back_u, k, ds)
+    backend = dist.get_backend(group)
+    if "nccl" not in str(backend) or not gather:
+        def compute_local(xs, ys, zs, *r):
+            return fresnel_sum(xs, ys, zs, *r, mode=mode, device=device)
+        out = _sharded_over_group(compute_local, x, y, z, rest, group, gather)
+        return out.cpu().numpy() if (was_numpy and _lib.is_torch(out)) else out
+    dx, dy, dz = (_lib.dev_f64(a, device) for a in (x, y, z))
+    sx, sy, sz = (_lib.dev_f64(a, device) for a in (u_back_x, u_back_y, u_back_z))
+    su = _lib.dev_c128(u_back_u, device)
+    if not (dx.shape == dy.shape == dz.shape and dx.dim() == 1):
+        raise ValueError("x, y, z must be 1-D arrays of equal length")
+    if not (sx.shape == sy.shape == sz.shape == su.shape and sx.dim() == 1):
+        raise ValueError("u_back_x, u_back_y, u_back_z, u_back_u must be 1-D arrays of equal length")
+    sd = None
+    if ds is not None:
+        sd = _lib.dev_f64(ds, device)
+        if sd.numel() != sx.numel():
+            sd = sd.expand(sx.shape).contiguous()
+    if broadcast_sources:  # the buffers are written by the broadcast: never alias the caller's arrays on ranks > 0
+        sx, sy, sz, su = (t.clone() if rank else t for t in (sx, sy, sz, su))
+        sd = sd.clone() if (sd is not None and rank) else sd
+    out = torch.empty(total, dtype=torch.complex128, device=device)
+    comm = _nccl_comm(group, device)
+    with torch.cuda.device(device):
+        rc = _lib.load().akb_fresnel_sum_sharded(
+            comm, rank, world, _lib.dev_ptr(dx), _lib.dev_ptr(dy), _lib.dev_ptr(dz), total,
+            _lib.dev_ptr(sx), _lib.dev_ptr(sy), _lib.dev_ptr(sz), _lib.dev_ptr(su),
+            _lib.dev_ptr(sd) if sd is not None else None, sx.shape[0], float(k), _lib.dev_ptr(out), int(mode),
+            1 if broadcast_sources else 0, _lib.torch_stream_ptr(device))
+    _lib.check(rc, "akb_fresnel_sum_sharded")
+    return out.cpu().numpy() if was_numpy else out
+
+
+def forward_propagation_cupy_batch_multi_gpu(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, devices=None,
+                                             mode=PHASE_FAITHFUL):
     """Drop-in for GPU0402:64-136 / GPU0402_multi.py:123-229.
 
-    * under torch.distributed (one process per GPU, world > 1): detector sharding + all-gather;
-    * otherwise, from ONE process: the detector blocks of ``array_split`` are launched on every
-      visible device back to back (the entry points are asynchronous, so no host thread per GPU
-      is needed as in GPU0402_multi.py:213-225) and gathered on the first device.
-    """
+    * under torch.distributed (one process per GPU, world > 1): ``fresnel_sum_sharded`` -- detector sharding,
+      NCCL all-gather, the full field on every rank;
+    * otherwise, from ONE process: the detector blocks of ``array_split`` are launched on every visible
+      device back to back (the entry points are asynchronous, so no host thread per GPU is needed as in
+      GPU0402_multi.py:213-225) and concatenated on the first device (GPU0402:135)."""
     import torch
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            return fresnel_sum_sharded(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds)
+            return fresnel_sum_sharded(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, mode=mode)
     except ImportError:  # pragma: no cover
         pass
-    was_numpy = not _any_torch(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, ds)
+    was_numpy = not _any_device(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, ds)
     if devices is None:
         devices = list(range(_lib.device_count()))
     if len(devices) <= 1:
-        return fresnel_sum(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds)
+        return fresnel_sum(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, mode=mode)
     total = int(x.shape[0])
     home = torch.device("cuda", devices[0])
     parts = []
@@ -175,8 +280,7 @@ def forward_propagation_cupy_batch_multi_gpu(x, y, z, u_back_x, u_back_y, u_back
         dev = torch.device("cuda", d)
         b, c = _lib.shard_range(total, len(devices), r)
         sl = slice(b, b + c)
-        parts.append(_fresnel_device(x[sl], y[sl], z[sl], u_back_x, u_back_y, u_back_z, u_back_u, k, ds,
-                                     PHASE_FAITHFUL, dev))
+        parts.append(_fresnel_device(x[sl], y[sl], z[sl], u_back_x, u_back_y, u_back_z, u_back_u, k, ds, mode, dev))
     out = torch.cat([p.to(home, non_blocking=True) for p in parts])
     if was_numpy:
         return out.cpu().numpy()
@@ -195,6 +299,7 @@ class WaveField3D:
 
     def __init__(self, num, _lambda, wave_num_H, wave_num_V, device=None):
         self._device = device
+        self.phase_mode = PHASE_FAITHFUL  # arithmetic of forward_propagation (the reference's roundings by default)
         if device is None:
             self.u = np.zeros(num, dtype=np.complex128)
             self.x = np.zeros(num, dtype=np.float64)
@@ -229,9 +334,13 @@ class WaveField3D:
         k = 2.0 * np.pi / self.lambda_  # CPU0402:39
         t0 = time.time()
         if self._device is None:
-            self.u = forward_propagation_numpy_batch(self.x, self.y, self.z, u_back.x, u_back.y, u_back.z,
-                                                     u_back.u, k, u_back.ds, num_cores=num_cores)
+            if self.phase_mode == PHASE_FAITHFUL:
+                self.u = forward_propagation_numpy_batch(self.x, self.y, self.z, u_back.x, u_back.y, u_back.z,
+                                                         u_back.u, k, u_back.ds, num_cores=num_cores)
+            else:
+                self.u = fresnel_sum(self.x, self.y, self.z, u_back.x, u_back.y, u_back.z, u_back.u, k, u_back.ds,
+                                     mode=self.phase_mode)
         else:
             self.u = forward_propagation_cupy_batch_multi_gpu(self.x, self.y, self.z, u_back.x, u_back.y,
-                                                              u_back.z, u_back.u, k, u_back.ds)
+                                                              u_back.z, u_back.u, k, u_back.ds, mode=self.phase_mode)
         print(f"計算時間: {time.time() - t0:.6f} 秒")

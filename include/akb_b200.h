@@ -33,6 +33,7 @@ extern "C" {
 #define AKB_OK 0
 #define AKB_ERR_ARG (-1)  /* bad argument (NULL pointer, negative size, ...) */
 #define AKB_ERR_CUDA (-2) /* CUDA runtime error, see akb_last_error() */
+#define AKB_ERR_NCCL (-3) /* NCCL missing or an NCCL call failed, see akb_last_error() */
 
 /* phase arithmetic of akb_fresnel_sum */
 #define AKB_PHASE_FAITHFUL 0 /* r and k*r rounded exactly like NumPy/numba (default) */
@@ -57,6 +58,9 @@ const char *akb_last_error(void);
 int akb_version(void);
 /* number of CUDA devices visible, <0 on error (replaces cp.cuda.runtime.getDeviceCount(), GPU0402:13) */
 int akb_device_count(void);
+/* Give the scratch memory cached for `device` (< 0: current device) back to the driver.  Synchronises the device.
+ * Scratch lives in the device's default stream-ordered pool with a release threshold of 4 GiB. */
+int akb_trim(int device);
 
 /* ------------------------------------------------------------------ path A
  * Huygens-Fresnel pair sum
@@ -72,7 +76,8 @@ int akb_device_count(void);
  *   src_ds     float64[N] or NULL (= 1)
  *   out        complex128[M]
  *   mode       AKB_PHASE_FAITHFUL | AKB_PHASE_EXACT | AKB_PHASE_REFERENCED
- * Domain: 0 <= k < 1e12 and k*r < 3.4e12 rad for every pair (the phase is reduced exactly as an integer
+ * Domain: |k| < 1e12 (k < 0 is evaluated as the conjugate problem, like the reference's exp(1j*(-k*dist)))
+ * and |k|*r < 3.4e12 rad for every pair (the phase is reduced exactly as an integer
  * multiple of 2*pi/4096 below 2^51; the reference's largest stage, 146 m at 1.35 nm, is 6.8e11 rad);
  * beyond that the result is undefined.  r = 0 yields NaN/inf like the
  * reference.  The summation order over j differs from the reference's (tiles, fixed-order partial sums):
@@ -92,6 +97,36 @@ int akb_fresnel_sum_host(const double *det_x, const double *det_y, const double 
  * over `nranks` devices exactly like cp.array_split (GPU0402:77-79): the first total%nranks
  * blocks hold one extra point. */
 int akb_shard_range(int64_t total, int nranks, int rank, int64_t *begin, int64_t *count);
+
+/* ------------------------------------------------------------------ path A on several GPUs
+ * forward_propagation_cupy_batch_multi_gpu (GPU0402:64-136; threaded twin GPU0402_multi.py:123-229 with
+ * process_on_gpu :64-121), for ONE process or host thread per GPU: rank `rank` of `nranks` computes its
+ * akb_shard_range block of the M detector points against the full source set, straight into its slot of
+ * `out`, and the blocks are all-gathered in place over NCCL (the replacement of cp.concatenate, GPU0402:135;
+ * ncclAllGather for equal blocks, one grouped ncclBroadcast per block otherwise).  On return (stream order)
+ * every rank holds the full complex128[M] field.
+ *   nccl_comm          an ncclComm_t (as void*) spanning the nranks devices: the caller's own, PyTorch's
+ *                      (ProcessGroupNCCL._comm_ptr()), or one made with akb_nccl_comm_init; may be NULL when nranks == 1
+ *   det_x/y/z          float64[M], the FULL detector arrays on every rank (the reference splits views of them)
+ *   src_*              as akb_fresnel_sum; with broadcast_sources != 0 rank 0's source arrays are first replicated
+ *                      into the other ranks' (caller-allocated) buffers with ncclBroadcast -- the reference keeps
+ *                      the back surface on device 0 and reads it by peer access (GPU0402:36-38)
+ * NCCL is bound at run time (the libnccl.so.2 already loaded in the process, else the default search path, else
+ * $AKB_NCCL_LIB); without it the call fails with AKB_ERR_NCCL when nranks > 1. */
+int akb_fresnel_sum_sharded(void *nccl_comm, int rank, int nranks, const double *det_x, const double *det_y,
+                            const double *det_z, int64_t M, double *src_x, double *src_y, double *src_z,
+                            double *src_u, double *src_ds, int64_t N, double k, double *out, int mode,
+                            int broadcast_sources, void *stream);
+
+/* In-place all-gather of akb_shard_range blocks: buf holds `total` items of `width` doubles each; on entry the
+ * block of `rank` is valid, on return (stream order) all of them are. */
+int akb_allgather_blocks(void *nccl_comm, int rank, int nranks, double *buf, int64_t total, int width, void *stream);
+
+/* Communicator helpers for callers that have none: rank 0 calls akb_nccl_unique_id and hands the 128 bytes to
+ * the other ranks by any means; every rank then calls akb_nccl_comm_init on its device (ncclCommInitRank). */
+int akb_nccl_unique_id(void *id128);
+int akb_nccl_comm_init(void **comm, int nranks, int rank, const void *id128);
+int akb_nccl_comm_destroy(void *comm);
 
 /* Measurement aid: with akb_fresnel_timing(1) every akb_fresnel_sum call of this thread records
  * CUDA events on its stream; akb_fresnel_last_timing() waits for the last call and returns the
@@ -156,11 +191,28 @@ int akb_intersect_reflect(const double *coeffs, const double *ray, const double 
  *   last_reflect [3][N] or NULL   (direction after the last mirror)
  *   det      [3][N] or NULL       (plane_ray_intersection of the last ray)
  *   dist     [K][N] or NULL       segment lengths |P_k - P_{k-1}| (BIG:2884-2897), P_{-1} = source
+ *   opl      [N] or NULL          optical path dist_0 + dist_1 + ... (+ |det - P_K| when a plane is given), summed
+ *                                 left to right like totalDist (BIG:3621-3623)
+ * HBM traffic per ray: 48 B in + 24 B per mirror + 24 (last_reflect) + 24 (det) + 8 K (dist) + 8 (opl) for the
+ * outputs requested; two rays per thread, streaming loads/stores.
  */
 int akb_trace_chain(const double *coeffs, const int *negative, int K, const double *plane,
                     const double *ray, const double *source, int64_t N, double *points, double *normals,
-                    double *reflects, double *last_reflect, double *det, double *dist,
+                    double *reflects, double *last_reflect, double *det, double *dist, double *opl,
                     unsigned skip_normalize, int *flags, void *stream);
+
+/* The tail of plot_result_debug(p, 'ray_wave') in one pass (BIG:3516-3558, 3611-3631; III_I:1867-1971): the last
+ * mirror's hit points and outgoing directions are rotated into the detector frame
+ *     v' = R_y (R_z v),   P' = R_y (R_z (P - pivot)) + pivot       (rotate_vectors / rotate_points, BIG:917-944)
+ * (rot_z = rot_y = NULL: no rotation), intersected with the plane x = plane_x and, when plane2_x != NULL, with
+ * the defocused plane x = *plane2_x (plane_ray_intersection with coeffs [0,..,1,0,0,-x]), and the optical path
+ *     opl = dist_0 + ... + dist_{K-1} + |det - P'|     (totalDist, BIG:3621-3623; opl2 with det2: totalDist2)
+ * is formed per ray.  rot_z, rot_y: row-major 3x3 (host); pivot: double[3] (host); dist: [K][N] segment lengths of
+ * akb_trace_chain (device; K = 0: only the last segment); every output may be NULL. */
+int akb_wavefront_opl(const double *last_point, const double *last_dir, const double *dist, int K, int64_t N,
+                      const double *rot_z, const double *rot_y, const double *pivot, double plane_x,
+                      const double *plane2_x, double *point_rot, double *dir_rot, double *det, double *det2,
+                      double *opl, double *opl2, void *stream);
 
 /* B geometries (K quadrics + one plane each) trace the SAME ray bundle in one launch: the pattern of the
  * focus / alignment scans auto_focus_NA (BIG:12746-12895: ~1600 calls of the tracer with 53x53 rays,
@@ -182,7 +234,7 @@ int akb_intersect_reflect_host(const double *coeffs, const double *ray, const do
 int akb_trace_chain_host(const double *coeffs, const int *negative, int K, const double *plane,
                          const double *ray, const double *source, int64_t N, double *points,
                          double *normals, double *reflects, double *last_reflect, double *det,
-                         double *dist, int *host_flags, int device);
+                         double *dist, double *opl, int *host_flags, int device);
 
 /* ------------------------------------------------------------------ hand-off helpers
  * calc_dS(points, ray_num_V, ray_num_H) -- AKB_raytrace_20250312.py:13418-13473. points (3,nV*nH). */

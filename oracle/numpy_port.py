@@ -115,6 +115,42 @@ def plane_ray_intersection(co, ray, src):
     return np.stack([t * L + P, t * M + Q, t * N + R])
 
 
+# ---------------------------------------------------------------- 'ray_wave' tail (row f-4)
+
+def rotate_vectors(vector, theta_y, theta_z):
+    """BIG:917-931: R_y @ (R_z @ v)."""
+    R_y = np.array([[np.cos(theta_y), 0, np.sin(theta_y)], [0, 1, 0], [-np.sin(theta_y), 0, np.cos(theta_y)]])
+    R_z = np.array([[np.cos(theta_z), -np.sin(theta_z), 0], [np.sin(theta_z), np.cos(theta_z), 0], [0, 0, 1]])
+    return R_y @ (R_z @ vector)
+
+
+def rotate_points(points, focus_apprx, theta_y, theta_z):
+    """BIG:933-944."""
+    shifted = points - focus_apprx[:, np.newaxis]
+    rotated = rotate_vectors(shifted, theta_y, theta_z)
+    rotated += focus_apprx[:, np.newaxis]
+    return rotated
+
+
+def wavefront_opl(last_point, last_dir, dist, plane_x, plane2_x, theta_y, theta_z, pivot):
+    """The tail of plot_result_debug(p,'ray_wave'): BIG:3589-3598 (rotation into the detector frame, plane),
+    BIG:3617-3631 (second plane, dist4tofocus, totalDist, totalDist2)."""
+    v = rotate_vectors(np.asarray(last_dir, np.float64), theta_y, theta_z)
+    p = rotate_points(np.asarray(last_point, np.float64), np.asarray(pivot, np.float64), theta_y, theta_z)
+    out = {"point": p, "dir": v}
+    for tag, px in (("", plane_x), ("2", plane2_x)):
+        co = np.zeros(10)
+        co[6] = 1
+        co[9] = -px
+        det = plane_ray_intersection(co, v, p)
+        total = dist[0]
+        for d in dist[1:]:
+            total = total + d
+        out["det" + tag] = det
+        out["opl" + tag] = total + np.linalg.norm(det - p, axis=0)
+    return out
+
+
 # ---------------------------------------------------------------- PSF (convenience row f-3)
 
 def compute_psf_fft(opd_m, amp, wavelength_m, pupil_dx_m, focal_length_m, pad_factor=2, window=None,

@@ -399,8 +399,138 @@ def gen_ray_mpmath(out, akb_chain):
           np.isfinite(np.delete(out["miss_P0"], 5, axis=1)).all())
 
 
+def gen_stagechain(out):
+    """SURVEY 8(f-1), pinned by RUNNING the reference end to end for a 25 x 25-ray KB and AKB case:
+      1. saveWaveData (BIG:13475-13654, executed from the AST-extracted defs; it ends in sys.exit()) writes the
+         hand-off folder output_<timestamp>/: every file is recorded, together with what the tracer handed to it
+         (mirror clouds, detector points of both planes) so that write_handoff can be tested on the same inputs;
+      2. the folder is renamed to the name CPU0402:192 hard-codes and the UNMODIFIED
+         Wavecalc_raytrace_fromData_CPU0402.py is run as __main__ (runpy, h5py stubbed) in that directory:
+         its complex_data_*.npz and the grids it re-saves are recorded.
+    wave_num is odd: saveWaveData only defines size_v1.. on its odd branch (BIG:13489-13504)."""
+    import datetime as _dt
+    import glob
+    import runpy
+    import shutil
+    import tempfile
+    n = 25
+    for kind in ("kb", "akb"):
+        ns = R.load_big(wave_num=n, option_AKB=(kind == "akb"))
+        ns["datetime"] = _dt.datetime
+        tracer = "plot_result_debug" if kind == "akb" else "KB_debug"
+        seen = {}
+        orig = ns[tracer]
+
+        def spy(*a, _orig=orig, **k):
+            seen["ret"] = _orig(*a, **k)
+            return seen["ret"]
+        ns[tracer] = spy
+        params = np.array(R.AKB_ALIGNMENT_PRESET) if kind == "akb" else np.zeros(26)
+        work = tempfile.mkdtemp(prefix=f"akb_handoff_{kind}_")
+        cwd = os.getcwd()
+        os.chdir(work)
+        try:
+            with R.quiet(), np.errstate(all="ignore"):
+                try:
+                    ns["saveWaveData"](params)
+                except SystemExit:
+                    pass
+            (folder,) = glob.glob("output_*")
+            ret = seen["ret"]
+            if kind == "akb":  # BIG:13479: source, vmirr_hyp, hmirr_hyp, vmirr_ell, hmirr_ell, detcenter, detcenter2, nH, nV, ...
+                clouds, det, det2, nH, nV = list(ret[1:5]), ret[5], ret[6], ret[7], ret[8]
+            else:              # BIG:13485: source, vmirr_hyp, hmirr_hyp, detcenter, detcenter2, nH, nV, ...
+                clouds, det, det2, nH, nV = list(ret[1:3]), ret[3], ret[4], ret[5], ret[6]
+            out[f"{kind}/tracer_source"] = np.asarray(ret[0], dtype=np.float64)
+            for i, c in enumerate(clouds):
+                out[f"{kind}/tracer_M{i + 1}"] = np.asarray(c, dtype=np.float64)
+            out[f"{kind}/tracer_det"], out[f"{kind}/tracer_det2"] = np.asarray(det), np.asarray(det2)
+            out[f"{kind}/ray_num"] = np.array([nV, nH])
+            out[f"{kind}/params"] = params
+            out[f"{kind}/handoff_listing"] = np.array(sorted(os.listdir(folder)))
+            for f in sorted(os.listdir(folder)):
+                if f.endswith(".npy"):
+                    out[f"{kind}/handoff/{f[:-4]}"] = np.load(os.path.join(folder, f))
+            out[f"{kind}/handoff/conditions_txt"] = np.array(open(os.path.join(folder, "calculation_conditions.txt")).read())
+            # ---- the Wavecalc script itself on that folder
+            os.rename(folder, "output_20250404_sNAAKB701")  # CPU0402:192
+            R._stub("h5py")
+            with R.quiet() as log, np.errstate(all="ignore"):
+                runpy.run_path(os.path.join(R.REF, "Wavecalc_raytrace_fromData_CPU0402.py"), run_name="__main__")
+            (res,) = [d for d in glob.glob("output_*") if d != "output_20250404_sNAAKB701"]
+            out[f"{kind}/wavecalc_listing"] = np.array(sorted(os.listdir(res)))
+            for f in sorted(os.listdir(res)):
+                path = os.path.join(res, f)
+                if f.endswith(".npz"):
+                    with np.load(path) as z:
+                        out[f"{kind}/wavecalc/{f[:-4]}"] = z["data"]
+                elif f.startswith("points_grid"):
+                    out[f"{kind}/wavecalc/{f[:-4]}"] = np.load(path)
+            img = out[f"{kind}/wavecalc/complex_data_Image"]
+            print(f"stagechain {kind}: hand-off {list(out[f'{kind}/handoff_listing'])}; wavecalc wrote "
+                  f"{list(out[f'{kind}/wavecalc_listing'])}; |Image| peak at {int(np.argmax(np.abs(img)))} of {img.size}")
+        finally:
+            os.chdir(cwd)
+            shutil.rmtree(work, ignore_errors=True)
+
+
+class _Stop(Exception):
+    pass
+
+
+def gen_ray_wave(out):
+    """plot_result_debug(p, 'ray_wave') (BIG:3565-3631) run from the AST-extracted defs with a 33 x 33
+    bundle.  The first griddata call of that branch (BIG:3665) is replaced by a spy that copies the caller's local
+    variables -- the rotation angles into the detector frame, the rotated bundle, both detector planes, totalDist,
+    totalDist2, DistError2 -- and stops the function there (what follows is interpolation, plotting, PSF)."""
+    n = 33
+    ns = R.load_big(wave_num=n, option_AKB=True)
+    calls = _record(ns, HOT)
+    grabbed = {}
+
+    def spy(*a, **k):
+        grabbed.update(sys._getframe(1).f_locals)
+        raise _Stop()
+    ns["griddata"] = spy
+    with R.quiet(), np.errstate(all="ignore"):
+        try:
+            ns["plot_result_debug"](np.array(R.AKB_ALIGNMENT_PRESET), "ray_wave", option_save=False)
+        except _Stop:
+            pass
+    L = grabbed
+    N = n * n
+    # the unrotated bundle after the 4th mirror: the LAST full-size intersect / reflect calls of the kept pass
+    last_int = [c for c in calls if c["fn"] == "mirr_ray_intersection" and c["args"][1].shape[1] == N][-1]
+    last_ref = [c for c in calls if c["fn"] == "reflect_ray" and c["args"][0].shape[1] == N][-1]
+    assert np.array_equal(last_int["out"], L["hmirr_hyp0"])
+    k = "akb"
+    out[f"{k}/last_point"], out[f"{k}/last_dir"] = last_int["out"], last_ref["out"]
+    out[f"{k}/dist"] = np.stack([L["dist0to1"], L["dist1to2"], L["dist2to3"], L["dist3to4"]])
+    out[f"{k}/theta_y"], out[f"{k}/theta_z"] = np.float64(-L["theta_y"]), np.float64(-L["theta_z"])  # rotate_*(.., -theta_y, -theta_z), BIG:3589-3591
+    out[f"{k}/pivot"] = np.asarray(L["focus_apprx"], dtype=np.float64)
+    out[f"{k}/plane_x"] = np.float64(L["s2f_middle"] + L["defocus"])
+    out[f"{k}/plane2_x"] = np.float64(L["s2f_middle"] + L["defocus"] + L["defocusWave"])
+    out[f"{k}/point_rot"], out[f"{k}/dir_rot"] = L["hmirr_hyp"], L["reflect4"]
+    out[f"{k}/det"], out[f"{k}/det2"] = L["detcenter"], L["detcenter2"]
+    out[f"{k}/opl"], out[f"{k}/opl2"] = L["totalDist"], L["totalDist2"]
+    out[f"{k}/DistError2"] = L["DistError2"]
+    print(f"ray_wave akb: n={n} theta_y={L['theta_y']:.3e} theta_z={L['theta_z']:.3e} totalDist mean {np.nanmean(L['totalDist']):.9f} "
+          f"std {np.nanstd(L['totalDist']):.3e}  defocusWave {L['defocusWave']}")
+
+
+SEPARATE = {"stagechain_ref": gen_stagechain, "ray_wave_ref": gen_ray_wave}  # fixtures added after round 1: `make_golden.py stagechain_ref`
+
+
 def main():
     assert R.available(), "needs /root/reference (build container only)"
+    if len(sys.argv) > 1:  # regenerate only the named fixtures
+        for name in sys.argv[1:]:
+            d = {}
+            SEPARATE[name](d)
+            path = os.path.join(HERE, name + ".npz")
+            np.savez_compressed(path, **{k.replace("/", "__"): v for k, v in d.items()})
+            print("wrote", path, os.path.getsize(path), "bytes")
+        return
     geo = {}
     files = {}
     for name, fn in (("fresnel_ref", gen_fresnel), ("dS_ref", gen_dS), ("psf_ref", gen_psf)):

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.akb_version() >= 100
+    assert lib.akb_version() >= 200
     assert isinstance(lib.akb_last_error(), bytes)
 
 
@@ -56,7 +56,13 @@ def test_argument_validation_needs_no_gpu(lib):
     from akbraytracing_b200 import _lib
     rc = lib.akb_fresnel_sum(None, None, None, -1, None, None, None, None, None, 0, 1.0, None, 0, None)
     assert rc == -1 and b"non-negative" in lib.akb_last_error()
-    rc = lib.akb_trace_chain(None, None, 0, None, None, None, 4, None, None, None, None, None, None, 0, None, None)
+    rc = lib.akb_trace_chain(None, None, 0, None, None, None, 4, None, None, None, None, None, None, None, 0, None, None)
+    assert rc == -1
+    rc = lib.akb_fresnel_sum_sharded(None, 2, 2, None, None, None, 4, None, None, None, None, None, 1, 1.0, None, 0, 0, None)
+    assert rc == -1 and b"rank" in lib.akb_last_error()
+    rc = lib.akb_fresnel_sum_sharded(None, 0, 2, None, None, None, 4, None, None, None, None, None, 1, 1.0, None, 0, 0, None)
+    assert rc == -1 and b"ncclComm_t" in lib.akb_last_error()
+    rc = lib.akb_wavefront_opl(None, None, None, 0, 4, None, None, None, 0.0, None, None, None, None, None, None, None, None)
     assert rc == -1
     with pytest.raises(RuntimeError):
         _lib.check(rc, "akb_trace_chain")

@@ -232,6 +232,48 @@ def test_fresnel_planar_row_blocks_match_general_loop_bitwise(akb, G, H, N):
         assert rel_l2(got[sel], oracle.fresnel_sum(x2[sel], y[sel], z[sel], sx, sy, sz, u, k, ds)) <= 1e-12
 
 
+def test_negative_and_zero_wave_number(akb):
+    """The reference accepts any k (phase = -k*dist, CPU0402:82): k < 0 is the conjugate problem, k = 0 a 1/r sum."""
+    from akbraytracing_b200 import workloads
+    c = workloads.c1_patch(n_src=3000, G=16)
+    for k in (-c["k"], 0.0, -1.0):
+        ref = oracle.fresnel_sum(c["x"], c["y"], c["z"], c["sx"], c["sy"], c["sz"], c["u"], k, c["ds"])
+        for mode in (akb.PHASE_FAITHFUL, akb.PHASE_EXACT, akb.PHASE_REFERENCED):
+            got = akb.fresnel_sum(c["x"], c["y"], c["z"], c["sx"], c["sy"], c["sz"], c["u"], k, c["ds"], mode=mode)
+            err = rel_l2(got, ref)
+            print(f"k = {k:.3e} mode {mode}: rel-L2 {err:.2e}")
+            assert err <= (1e-12 if mode == akb.PHASE_FAITHFUL else FIELD_TOL / 10)
+
+
+class _CudaArray:
+    """What a CuPy / Numba device array looks like to a consumer: __cuda_array_interface__, shape, slicing."""
+
+    def __init__(self, t):
+        self._t = t
+        self.shape = tuple(t.shape)
+        self.__cuda_array_interface__ = t.__cuda_array_interface__
+
+    def __getitem__(self, sl):
+        return _CudaArray(self._t[sl])
+
+
+def test_cuda_array_interface_inputs_are_used_in_place(akb, torch, golden):
+    """GPU0402:36-38 holds cp.ndarrays: any object with __cuda_array_interface__ is a device array here
+    (zero copy: the result is the same as for the torch tensors that own the memory)."""
+    c = golden("fresnel_ref").group("mirror_to_mirror")
+    t = {k: torch.as_tensor(np.ascontiguousarray(v)).cuda() for k, v in c.items() if k not in ("k", "ref", "ref_numpy")}
+    w = {k: _CudaArray(v) for k, v in t.items()}
+    assert akb._lib.from_cuda_array(w["sx"]).data_ptr() == t["sx"].data_ptr()
+    for fn in (akb.forward_propagation_cupy_batch, akb.forward_propagation_cupy_batch_multi_gpu):
+        got = fn(w["x"], w["y"], w["z"], w["sx"], w["sy"], w["sz"], w["u"], float(c["k"]), w["ds"])
+        assert got.is_cuda and hasattr(got, "__cuda_array_interface__")
+        assert rel_l2(got.cpu().numpy(), c["ref"]) <= 1e-12
+    g = golden("ray_er3d_ref")
+    ray, src = _CudaArray(torch.as_tensor(g["single/ray"]).cuda()), _CudaArray(torch.as_tensor(g["general/source"]).cuda())
+    p, n, r = akb.intersect_reflect(g["general/coeffs"], ray, src)
+    assert p.is_cuda and np.array_equal(p.cpu().numpy(), g["general/points"]) and np.array_equal(r.cpu().numpy(), g["general/reflect"])
+
+
 def test_fresnel_empty_inputs(akb):
     e = np.zeros(0)
     x = np.array([0.1, 0.2])
@@ -382,25 +424,27 @@ def test_chain_host_abi_and_miss_semantics(akb, golden):
     ray0 = np.ascontiguousarray(g["ray0"])
     co = np.ascontiguousarray(g["coeffs"]); neg = np.ascontiguousarray(g["negative"].astype(np.int32))
     plane = np.ascontiguousarray(g["plane"])
-    pts = np.empty((4, 3, N)); last = np.empty((3, N)); det = np.empty((3, N)); dist = np.empty((4, N))
+    pts = np.empty((4, 3, N)); last = np.empty((3, N)); det = np.empty((3, N)); dist = np.empty((4, N)); opl = np.empty(N)
     flags = np.zeros(4, np.int32)
     hp = akb._lib.host_ptr
     rc = akb._lib.load().akb_trace_chain_host(hp(co), hp(neg), 4, hp(plane), hp(ray0), hp(src), N, hp(pts), None, None,
-                                              hp(last), hp(det), hp(dist), hp(flags), 0)
+                                              hp(last), hp(det), hp(dist), hp(opl), hp(flags), 0)
     akb._lib.check(rc, "akb_trace_chain_host")
     assert flags[0] == 0
     for k in range(4):
         assert np.array_equal(pts[k], g[f"P{k}"])
     assert np.array_equal(det, g["det"])
+    total = ((dist[0] + dist[1]) + dist[2]) + dist[3] + np.linalg.norm(det - pts[3], axis=0)   # BIG:3621-3623
+    assert np.array_equal(opl, total)
     # make one ray miss the THIRD mirror only is hard to construct; make it miss the first:
     ray_bad = ray0.copy()
     ray_bad[:, 7] = [-1.0, 0.0, 0.0]
     rc = akb._lib.load().akb_trace_chain_host(hp(co), hp(neg), 4, hp(plane), hp(ray_bad), hp(src), N, hp(pts), None,
-                                              None, hp(last), hp(det), hp(dist), hp(flags), 0)
+                                              None, hp(last), hp(det), hp(dist), hp(opl), hp(flags), 0)
     akb._lib.check(rc, "akb_trace_chain_host")
     ref = oracle.trace_chain(list(co), list(neg), plane, ray_bad, src)
     if np.isnan(ref["points"][0]).all():
-        assert flags[0] > 0 and np.isnan(pts).all() and np.isnan(det).all()
+        assert flags[0] > 0 and np.isnan(pts).all() and np.isnan(det).all() and np.isnan(opl).all()
     else:  # the reversed ray still hits the first quadric somewhere: results must simply agree
         assert np.array_equal(pts[0], ref["points"][0])
 
@@ -467,15 +511,6 @@ def test_opl_to_field(akb):
     assert np.abs(got - ref).max() <= 2e-15 * 1.5 + 1e-15
 
 
-def test_single_process_multi_device(akb, torch, golden):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 visible GPUs")
-    c = golden("fresnel_ref").group("patch_euv")
-    got = akb.forward_propagation_cupy_batch_multi_gpu(c["x"], c["y"], c["z"], c["sx"], c["sy"], c["sz"], c["u"],
-                                                       float(c["k"]), c["ds"])
-    assert rel_l2(got, c["ref"]) <= 1e-12
-
-
 # ------------------------------------------------------------------ next rows: PSF, stage chain
 
 @pytest.mark.parametrize("tag,kw", [("plain", dict(pad_factor=2)),
@@ -489,10 +524,95 @@ def test_psf_on_device_vs_reference_golden(akb, torch, golden, tag, kw):
     assert It.is_cuda and np.allclose(It.cpu().numpy(), g[f"{tag}/I"], rtol=1e-10, atol=1e-16)
 
 
+def _write_reference_handoff(g, kind, folder):
+    """Re-create on disk the folder the reference's saveWaveData wrote (arrays and text from the golden)."""
+    import os
+    os.makedirs(folder, exist_ok=True)
+    for name in g[f"{kind}/handoff_listing"]:
+        name = str(name)
+        if name.endswith(".npy"):
+            np.save(os.path.join(folder, name), g[f"{kind}/handoff/{name[:-4]}"])
+    with open(os.path.join(folder, "calculation_conditions.txt"), "w") as fh:
+        fh.write(str(g[f"{kind}/handoff/conditions_txt"]))
+
+
+@pytest.mark.parametrize("kind,K", [("kb", 2), ("akb", 4)])
+def test_write_handoff_matches_saveWaveData(akb, golden, tmp_path, kind, K):
+    """write_handoff on what the reference's tracer returned vs the folder the reference's saveWaveData wrote
+    from it (BIG:13475-13654, run here at golden time): same file list, same arrays (dS to 1e-12), same
+    calculation_conditions.txt line for line."""
+    import os
+    g = golden("stagechain_ref")
+    nV, nH = (int(v) for v in g[f"{kind}/ray_num"])
+    clouds = [g[f"{kind}/tracer_M{i + 1}"] for i in range(K)]
+    text = str(g[f"{kind}/handoff/conditions_txt"])
+    stamp = [l for l in text.splitlines() if l.startswith("time:")][0].split(": ")[1]
+    akb.write_handoff(str(tmp_path), g[f"{kind}/tracer_source"], clouds, (nV, nH), g[f"{kind}/tracer_det"],
+                      det_defocus=g[f"{kind}/tracer_det2"], option_AKB=(K == 4), option_HighNA=True, defocus=1e-3,
+                      initial_params=g[f"{kind}/params"], timestamp=stamp)
+    assert sorted(os.listdir(tmp_path)) == [str(n) for n in g[f"{kind}/handoff_listing"]]
+    for name in g[f"{kind}/handoff_listing"]:
+        name = str(name)
+        if not name.endswith(".npy"):
+            continue
+        got, ref = np.load(tmp_path / name), g[f"{kind}/handoff/{name[:-4]}"]
+        assert got.shape == ref.shape and got.dtype == ref.dtype, name
+        if name.startswith("points_M"):
+            assert np.array_equal(got[:3], ref[:3]), name
+            assert np.allclose(got[3], ref[3], rtol=1e-12, atol=0), name   # dS: device kernel vs calc_dS
+        else:
+            assert np.array_equal(got, ref), name
+    assert open(tmp_path / "calculation_conditions.txt").read() == text
+    # zero / negative defocus: no defocused grid (BIG:13593), signed half-size otherwise (BIG:13594-13599)
+    akb.write_handoff(str(tmp_path / "z"), g[f"{kind}/tracer_source"], clouds, (nV, nH), g[f"{kind}/tracer_det"],
+                      det_defocus=g[f"{kind}/tracer_det2"], defocus=0.0)
+    assert not os.path.exists(tmp_path / "z" / "points_gridDefocus.npy")
+    akb.write_handoff(str(tmp_path / "n"), g[f"{kind}/tracer_source"], clouds, (nV, nH), g[f"{kind}/tracer_det"],
+                      det_defocus=g[f"{kind}/tracer_det2"], defocus=-1e-3)
+    gneg = np.load(tmp_path / "n" / "points_gridDefocus.npy")
+    half = 2e-7 + (-1e-3) * 0.082 * 2
+    assert np.isclose(gneg[1].max() - gneg[1].min(), abs(2 * half), rtol=1e-9) and gneg[1, 0] > gneg[1, 1]  # reversed axis
+
+
+@pytest.mark.parametrize("kind,K", [("kb", 2), ("akb", 4)])
+def test_stage_chain_matches_reference_script(akb, golden, tmp_path, kind, K):
+    """run_stage_chain on the folder the reference wrote vs what the UNMODIFIED Wavecalc_raytrace_fromData_CPU0402.py
+    computed from it as __main__ (CPU0402:190-377, run at golden time): every complex_data_*.npz, the stretched
+    focal grid it saves, the file list of its output folder."""
+    import os
+    g = golden("stagechain_ref")
+    folder = tmp_path / "output_20250404_sNAAKB701"
+    _write_reference_handoff(g, kind, str(folder))
+    out = akb.run_stage_chain(str(folder), out_dir=str(tmp_path / "out"))
+    stages = [f"M{i + 1}" for i in range(K)] + ["Image", "Image2"]
+    assert list(out) == stages
+    for name in stages:
+        ref = g[f"{kind}/wavecalc/complex_data_{name}"]
+        err = rel_l2(out[name], ref)
+        print(f"{kind} stage {name}: rel-L2 vs the reference script = {err:.2e}")
+        assert err <= FIELD_TOL and err <= 1e-11
+        assert int(np.argmax(np.abs(out[name]) ** 2)) == int(np.argmax(np.abs(ref) ** 2))
+        with np.load(tmp_path / "out" / f"complex_data_{name}.npz") as z:
+            assert np.array_equal(z["data"], out[name])
+    assert sorted(os.listdir(tmp_path / "out")) == [str(n) for n in g[f"{kind}/wavecalc_listing"]]
+    for name in ("points_gridImage", "points_gridImage2"):
+        assert np.array_equal(np.load(tmp_path / "out" / f"{name}.npy"), g[f"{kind}/wavecalc/{name}"]), name
+    # resume: a stored M1 is loaded instead of recomputed (CPU0402:261-265); fields may stay on the device
+    again = akb.run_stage_chain(str(folder), resume_dir=str(tmp_path / "out"), keep_on_device=True)
+    assert again["M1"].is_cuda and np.array_equal(again["M1"].cpu().numpy(), out["M1"])
+    assert rel_l2(again["Image"].cpu().numpy(), out["Image"]) <= 1e-13
+    # per-stage automatic phase arithmetic: EXACT where k r 2^-52 is small, still inside the parity gate
+    auto = akb.run_stage_chain(str(folder), phase_mode="auto")
+    for name in stages:
+        err = rel_l2(auto[name], g[f"{kind}/wavecalc/complex_data_{name}"])
+        print(f"{kind} stage {name} (auto phase mode): rel-L2 {err:.2e}")
+        assert err <= FIELD_TOL / 10
+
+
 @pytest.mark.parametrize("tag,K", [("c3", 2), ("c4", 4)])
-def test_stage_chain_files_and_fields(akb, torch, tmp_path, tag, K):
-    """trace -> write_handoff (reference file formats) -> run_stage_chain with device-resident fields,
-    checked stage by stage against the oracle (the chain of CPU0402:247-375)."""
+def test_stage_chain_from_own_trace(akb, torch, tmp_path, tag, K):
+    """trace -> write_handoff -> run_stage_chain with device-resident fields on OUR traced clouds (even ray
+    count, separate focal-grid size: the paths the reference cannot take), stage by stage against the oracle."""
     from akbraytracing_b200 import workloads
     n, G = 24, 12
     coeffs, neg, plane, ray, src = workloads.chain_inputs(tag, n, "cuda")
@@ -503,28 +623,43 @@ def test_stage_chain_files_and_fields(akb, torch, tmp_path, tag, K):
     h = akb.load_handoff(str(folder))
     assert h["conditions"]["option_AKB"] == (K == 4) and len(h["mirrors"]) == K
     assert h["mirrors"][0].shape == (4, n * n) and h["gridImage"].shape == (3, G * G)
-    dS_ref = oracle.calc_dS(h["mirrors"][0][:3], n, n)
-    assert np.allclose(h["mirrors"][0][3].reshape(n, n), dS_ref, rtol=1e-12, atol=0)
-    out = akb.run_stage_chain(str(folder), out_dir=str(tmp_path / "out"))
-    # oracle chain
+    out = akb.run_stage_chain(str(folder))
     k = 2 * np.pi / 13.5e-9
     u = np.ones(1, complex); bx, by, bz = (np.array([v]) for v in h["source"]); ds = np.ones(1)
     for i, pts in enumerate(h["mirrors"]):
         u = oracle.fresnel_sum(pts[0], pts[1], pts[2], bx, by, bz, u, k, ds)
-        err = rel_l2(out[f"M{i + 1}"], u)
-        assert err <= 1e-11, (i, err)
+        assert rel_l2(out[f"M{i + 1}"], u) <= 1e-11
         bx, by, bz, ds = pts[0], pts[1], pts[2], pts[3]
-    grid = h["gridImage"]
-    mean = grid.mean(axis=1, keepdims=True)
-    grid = (grid - mean) * 2.0 + mean
-    ref = oracle.fresnel_sum(grid[0], grid[1], grid[2], bx, by, bz, u, k, ds)
-    assert rel_l2(out["Image"], ref) <= 1e-10
-    assert int(np.argmax(np.abs(out["Image"]))) == int(np.argmax(np.abs(ref)))
-    with np.load(tmp_path / "out" / "complex_data_Image.npz") as z:
-        assert np.array_equal(z["data"], out["Image"])
-    # resume: a stored M1 is loaded instead of recomputed (CPU0402:261-265)
-    again = akb.run_stage_chain(str(folder), resume_dir=str(tmp_path / "out"))
-    assert np.array_equal(again["M1"], out["M1"]) and rel_l2(again["Image"], out["Image"]) <= 1e-13
+
+
+def test_chain_opl_and_ray_wave_tail(akb, torch, golden):
+    """opl output of the fused chain = the reference's totalDist (BIG:3621-3623), and wavefront_opl = the tail of
+    plot_result_debug(p,'ray_wave') recorded from the reference run (rotation into the detector frame, two planes,
+    totalDist / totalDist2)."""
+    g = golden("chain_akb_ref")
+    n = g["tan_h"].shape[0]
+    src = np.repeat(g["source_point"][:, None], n * n, axis=1)
+    out = akb.trace_chain(list(g["coeffs"]), list(g["negative"]), g["plane"], g["ray0"], src, want_opl=True)
+    total = ((g["dist0"] + g["dist1"]) + g["dist2"]) + g["dist3"] + np.linalg.norm(out["det"] - out["points"][3], axis=0)
+    assert np.allclose(out["opl"], total, rtol=2e-16, atol=0)
+    only = akb.trace_chain(list(g["coeffs"]), list(g["negative"]), None, g["ray0"], src, want_dist=False, want_opl=True)
+    assert np.allclose(only["opl"], ((g["dist0"] + g["dist1"]) + g["dist2"]) + g["dist3"], rtol=2e-16, atol=0)
+    w = golden("ray_wave_ref")
+    for kind in ("akb",):
+        got = akb.wavefront_opl(w[f"{kind}/last_point"], w[f"{kind}/last_dir"], w[f"{kind}/dist"], float(w[f"{kind}/plane_x"]),
+                                plane2_x=float(w[f"{kind}/plane2_x"]), theta_y=float(w[f"{kind}/theta_y"]),
+                                theta_z=float(w[f"{kind}/theta_z"]), pivot=w[f"{kind}/pivot"], want_rotated=True)
+        for key, ref in (("point", "point_rot"), ("dir", "dir_rot"), ("det", "det"), ("det2", "det2")):
+            err = per_ray_rel(got[key], w[f"{kind}/{ref}"])
+            print(f"ray_wave {key}: per-ray rel {err:.2e}")
+            assert err <= RAY_TOL
+        for key in ("opl", "opl2"):
+            err = float(np.abs(got[key] / w[f"{kind}/{key}"] - 1).max())
+            print(f"ray_wave {key}: max rel {err:.2e}")
+            assert err <= RAY_TOL
+        # the wavefront error map input (nm): DistError2 = (totalDist2 - mean) * 1e9, BIG:3631
+        de2 = (got["opl2"] - np.nanmean(got["opl2"])) * 1e9
+        assert np.abs(de2 - w[f"{kind}/DistError2"]).max() <= 1e-3   # 1e-12 m of 146 m: a picometre
 
 
 # ------------------------------------------------------------------ production sizes, threads, host ABI

@@ -162,3 +162,55 @@ def test_array_split_bounds():
             ref = np.array_split(np.arange(total), parts)
             assert [n for _, n in b] == [len(r) for r in ref]
             assert all(s == (r[0] if len(r) else s) for (s, _), r in zip(b, ref))
+
+
+# ------------------------------------------------------------------ rows f-1 / f-4: reference END-TO-END runs
+
+@pytest.mark.parametrize("kind,K", [("kb", 2), ("akb", 4)])
+def test_oracle_stage_chain_reproduces_the_reference_script(golden, kind, K):
+    """The unmodified Wavecalc_raytrace_fromData_CPU0402.py was run as __main__ on a folder written by the
+    reference's saveWaveData (tests/golden/make_golden.py stagechain_ref).  The oracle, chained the way the script
+    chains its stages (CPU0402:247-375: ds of a surface = row 3 of its points file, focal grid stretched by 2,
+    defocused grid 'stretched' by 1), reproduces every complex_data_*.npz bit for bit."""
+    g = golden("stagechain_ref")
+    from akbraytracing_b200.stagechain import parse_conditions
+    cond = parse_conditions(str(g[f"{kind}/handoff/conditions_txt"]))
+    assert cond["option_AKB"] == (K == 4) and cond["option_HighNA"] is True
+    nV, nH = (int(v) for v in g[f"{kind}/ray_num"])
+    assert (cond["ray_num_H1"], cond["ray_num_V1"], cond["pix_y"], cond["pix_z"]) == (nH, nV, nH, nV)
+    k = 2.0 * np.pi / np.float64(13.5e-9)
+    src = g[f"{kind}/handoff/points_source"]
+    u = np.ones(1, complex); bx, by, bz = (np.array([v]) for v in src); ds = np.ones(1)
+    for i in range(K):
+        pts = g[f"{kind}/handoff/points_M{i + 1}"]
+        u = oracle.fresnel_sum(pts[0], pts[1], pts[2], bx, by, bz, u, k, ds)
+        assert np.array_equal(u, g[f"{kind}/wavecalc/complex_data_M{i + 1}"]), f"stage M{i + 1}"
+        bx, by, bz, ds = pts[0], pts[1], pts[2], pts[3]
+    for name, grid_name, scale in (("Image", "points_gridImage", 2.0), ("Image2", "points_gridDefocus", 1.0)):
+        grid = np.array(g[f"{kind}/handoff/{grid_name}"])
+        for r in range(3):
+            m = np.mean(grid[r, :])
+            grid[r, :] = (grid[r, :] - m) * scale + m if scale != 1.0 else (grid[r, :] - m) + m
+        saved = "points_gridImage" if name == "Image" else "points_gridImage2"
+        assert np.array_equal(grid, g[f"{kind}/wavecalc/{saved}"])
+        f = oracle.fresnel_sum(grid[0], grid[1], grid[2], bx, by, bz, u, k, ds)
+        assert np.array_equal(f, g[f"{kind}/wavecalc/complex_data_{name}"]), name
+    # the hand-off arrays themselves: dS row = oracle.calc_dS of the cloud, rows 0-2 = what the tracer returned
+    for i in range(K):
+        pts = g[f"{kind}/handoff/points_M{i + 1}"]
+        assert np.array_equal(pts[:3], g[f"{kind}/tracer_M{i + 1}"])
+        assert np.allclose(pts[3].reshape(nV, nH), oracle.calc_dS(pts[:3], nV, nH), rtol=1e-12, atol=0)
+
+
+def test_oracle_ray_wave_tail_reproduces_the_reference_driver(golden):
+    """plot_result_debug(p,'ray_wave') run from the reference (make_golden.py ray_wave_ref): rotation into the
+    detector frame, both planes, totalDist / totalDist2 from the NumPy restatement."""
+    w = golden("ray_wave_ref")
+    k = "akb"
+    got = npp.wavefront_opl(w[f"{k}/last_point"], w[f"{k}/last_dir"], w[f"{k}/dist"], float(w[f"{k}/plane_x"]),
+                                   float(w[f"{k}/plane2_x"]), float(w[f"{k}/theta_y"]), float(w[f"{k}/theta_z"]), w[f"{k}/pivot"])
+    for key, ref in (("point", "point_rot"), ("dir", "dir_rot"), ("det", "det"), ("det2", "det2"), ("opl", "opl"), ("opl2", "opl2")):
+        assert np.array_equal(got[key], w[f"{k}/{ref}"]), key
+    # segment lengths of the chain = what the fused kernel's dist output must give (oracle.trace_chain)
+    c = golden("chain_akb_ref")
+    assert w[f"{k}/dist"].shape[0] == 4

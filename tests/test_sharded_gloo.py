@@ -1,7 +1,9 @@
 """World-size-2/3 gloo tests (CPU) of the multi-GPU host logic: array_split sharding of the
-detector points, equal-size padded all-gather, reassembly.  The per-rank compute is injected
-(the CPU oracle) because there is no GPU here; on the GPU box the same code path runs the CUDA
-kernel over NCCL (bench.py --gpus N)."""
+detector points, equal-size padded all-gather, reassembly.  The per-rank compute handed to the
+private helper wavecalc._sharded_over_group is the CPU oracle because there is no GPU here; the
+product entry (fresnel_sum_sharded) passes the CUDA call to the same helper on gloo groups and runs
+akb_fresnel_sum_sharded (block kernel + in-place NCCL all-gather) on NCCL groups -- that path is covered
+on hardware by tests/test_multi_gpu.py and bench.py --gpus N."""
 import os
 import socket
 
@@ -42,12 +44,18 @@ def _worker(rank, world, port, M, out_dir):
             seen["count"] = len(xs)
             return oracle.fresnel_sum(xs, ys, zs, *rest[:4], rest[4], rest[5], nthreads=1)
 
-        full = wavecalc.fresnel_sum_sharded(x, y, z, sx, sy, sz, u, k, ds, compute=compute)
+        full = wavecalc._sharded_over_group(compute, x, y, z, (sx, sy, sz, u, k, ds), None, True)
         ref = oracle.fresnel_sum(x, y, z, sx, sy, sz, u, k, ds, nthreads=1)
         ok = full.shape[0] == M and np.array_equal(full.numpy(), ref)
         expect = len(np.array_split(np.arange(M), world)[rank])
         ok = ok and seen["count"] == expect
-        local = wavecalc.fresnel_sum_sharded(x, y, z, sx, sy, sz, u, k, ds, compute=compute, gather=False)
+        local = wavecalc._sharded_over_group(compute, x, y, z, (sx, sy, sz, u, k, ds), None, False)
+        # the product entry point has no injection seam, and without a GPU it must fail loudly, not fall back
+        try:
+            wavecalc.fresnel_sum_sharded(x, y, z, sx, sy, sz, u, k, ds)
+            ok = ok and torch.cuda.is_available()
+        except (RuntimeError, AssertionError):
+            pass
         ok = ok and len(local) == expect
         with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as fh:
             fh.write("ok" if ok else f"mismatch shape={tuple(full.shape)} count={seen}")

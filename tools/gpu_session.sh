@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box session: smoke, parity tests, the bench line (both arms), the ncu launch list and a full capture of the pair kernel.
-TAG=${TAG:-r01h}
+TAG=${TAG:-r02}
 mkdir -p gpurun_out
 python __graft_entry__.py --smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke exit $?"; tail -1 gpurun_out/smoke_$TAG.log
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu_$TAG.log
