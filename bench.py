@@ -5,18 +5,21 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One step = one pass of the hot path over one synthetic batch, inputs resident in HBM:
-  KB two-mirror trace of 1000x1000 rays (fused chain kernel) -> calc_dS -> exp(-ik OPL)
+  mirror chain trace of 1000x1000 rays (fused chain kernel) -> calc_dS -> exp(-ik OPL)
   -> Fresnel pair sum of the 1e6 last-mirror points onto the focal grid.
-N = 1: BASELINE config C3 (1e6 rays -> 512x512 grid, 2.6e11 terms per step).
-N > 1: weak scaling -- every rank holds a 512x512 block of a 512 x (512 N) grid (N = 8 is half of
-C4's 2048x2048 detector), the source set is replicated, detector blocks are array_split
-contiguous blocks, and the step ends with the NCCL all-gather of the field.
+N = 1: BASELINE config C3 (KB two-mirror trace, 1e6 rays -> 512x512 grid, 2.6e11 terms per step), the largest
+       single-GPU configuration.
+N > 1: BASELINE config C4 as written (AKB four-mirror trace, 1e6 rays x a FIXED 2048x2048 detector = 4.2e12 terms per
+       step, STRONG scaling): every rank passes the full grid to the reference-shaped multi-GPU call
+       forward_propagation_cupy_batch_multi_gpu -> fresnel_sum_sharded -> akb_fresnel_sum_sharded, which computes
+       the rank's array_split block and all-gathers the blocks in place over NCCL.  Before timing, every rank checks
+       the gathered field against the CPU oracle on 256 random detector points, its bit-equality across ranks, and
+       an uneven case (M not divisible by N); the outcome is the `parity` block of the JSON line.
 
-Prints ONE JSON line (rank 0).  `value` = terms of all ranks / max-over-ranks device time.
-`e2e` = the same stage through the reference-facing host-buffer call
-(forward_propagation_numpy_batch -> akb_fresnel_sum_host: H2D + kernels + D2H inside).
-`--impl reference` times the CPU restatement of the reference's numba path (oracle/, all host
-threads) on a bounded detector subset of the same workload.
+Prints ONE JSON line (rank 0).  `value` = terms of the whole job / max-over-ranks device time.
+`e2e` = the same stage through the reference-facing call with HOST (NumPy) buffers: H2D + kernels (+ all-gather)
++ D2H inside the timed region.  `--impl reference` times the CPU restatement of the reference's numba path (oracle/,
+all host threads) on a bounded detector subset of the same workload.
 """
 from __future__ import annotations
 
@@ -34,15 +37,27 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-GRID = 512            # focal grid side per rank
 RAYS = 1000           # ray grid side -> 1e6 source points
 WAVELENGTH = 13.5e-9  # CPU0402:243
 ALG_FLOP_PER_TERM = 23.0   # SURVEY.md 8(d) convention
-# Counted in the SASS of the loop this workload runs (faithful mode, planar-row blocks: the focal grid is a
-# plane x = const whose rows align with the 4 points of a thread; tools/sass_cost.py), per pair:
-# 14 DFMA (x2) + 8.25 DMUL + 5.25 DADD.  (General loop, irregular detector sets: 14 + 10 + 7 = 31 instr, 45 flop.)
-EXEC_FLOP_PER_TERM = 41.5
-FP64_INSTR_PER_TERM = 27.5  # each occupies the FP64 pipe of an SM sub-partition for >= 2 cycles
+
+
+def workload(n_gpus):
+    """(geometry tag, mirrors, focal grid side) of the configuration this run measures."""
+    return ("c3", 2, 512) if n_gpus == 1 else ("c4", 4, 2048)
+
+
+def workload_config(n_gpus):
+    tag, K, G = workload(n_gpus)
+    if n_gpus == 1:
+        name = "C3: KB two-mirror trace of 1e6 rays + Fresnel sum onto a 512x512 focal grid, 1 GPU"
+    else:
+        name = (f"C4: AKB four-mirror trace of 1e6 rays + Fresnel sum onto a fixed 2048x2048 detector, array_split over "
+                f"{n_gpus} GPUs through forward_propagation_cupy_batch_multi_gpu (akb_fresnel_sum_sharded: block kernel + "
+                f"in-place NCCL all-gather), strong scaling")
+    return {"workload": name, "rays": RAYS * RAYS, "mirrors": K, "detector_points": G * G,
+            "terms_per_step": float(RAYS * RAYS) * G * G, "wavelength_m": WAVELENGTH,
+            "phase_mode": "faithful", "l2": "flushed between timed steps (256 MiB write)"}
 
 
 def measured_peaks():
@@ -104,25 +119,28 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------ reference arm
 
-def cpu_workload(n_rays=RAYS):
-    """The same C3 source set, built WITHOUT the CUDA library: oracle chain trace + oracle calc_dS."""
+def cpu_workload(n_gpus, n_rays=RAYS):
+    """The same source set and focal grid, built WITHOUT the CUDA library: oracle chain trace + oracle calc_dS."""
     import oracle
+    tag, K, G = workload(n_gpus)
     geo = np.load(os.path.join(ROOT, "akbraytracing_b200", "data", "geometry.npz"))
-    tan_h, tan_v = geo["c3__tan_h"], geo["c3__tan_v"]
+    tan_h, tan_v = geo[f"{tag}__tan_h"], geo[f"{tag}__tan_v"]
     n = n_rays
     raw = np.vstack([np.ones(n * n), np.tile(tan_h, n), np.repeat(tan_v, n)])
     ray = oracle.normalize_vector(raw)
-    src = np.repeat(geo["c3__source_point"][:, None], n * n, axis=1)
-    tr = oracle.trace_chain(list(geo["c3__coeffs"]), [bool(b) for b in geo["c3__negative"]], geo["c3__plane"], ray, src)
+    src = np.repeat(geo[f"{tag}__source_point"][:, None], n * n, axis=1)
+    tr = oracle.trace_chain(list(geo[f"{tag}__coeffs"]), [bool(b) for b in geo[f"{tag}__negative"]], geo[f"{tag}__plane"], ray, src)
     last = tr["points"][-1]
     k = 2.0 * np.pi / WAVELENGTH
-    opl = tr["dist"][0] + tr["dist"][1]
+    opl = tr["dist"][0]
+    for d in tr["dist"][1:]:
+        opl = opl + d
     u = np.exp(-1j * (k * opl))
     ds = oracle.calc_dS(last, n, n).ravel()
     det = tr["det"]
     yc, zc = (det[1].min() + det[1].max()) / 2, (det[2].min() + det[2].max()) / 2
-    yy, zz = np.meshgrid(np.linspace(yc - 1e-6, yc + 1e-6, GRID), np.linspace(zc - 1e-6, zc + 1e-6, GRID))
-    return dict(det_x=np.full(GRID * GRID, det[0].mean()), det_y=yy.ravel(), det_z=zz.ravel(),
+    yy, zz = np.meshgrid(np.linspace(yc - 1e-6, yc + 1e-6, G), np.linspace(zc - 1e-6, zc + 1e-6, G))
+    return dict(det_x=np.full(G * G, det[0].mean()), det_y=yy.ravel(), det_z=zz.ravel(),
                 src_x=np.ascontiguousarray(last[0]), src_y=np.ascontiguousarray(last[1]),
                 src_z=np.ascontiguousarray(last[2]), u=u, ds=ds, k=k)
 
@@ -151,10 +169,11 @@ def cpu_baseline(target_s=12.0):
     import oracle
     oracle.build()
     threads = host_threads()
-    w = cpu_workload()
+    w = cpu_workload(1)
+    total = w["det_x"].shape[0]
     time_cpu_sample(w, max(threads, 16), threads)            # warms the thread pool
     rate, _ = time_cpu_sample(w, 4 * max(threads, 16), threads)  # calibration
-    n_det = int(min(GRID * GRID, max(threads, rate * target_s / w["src_x"].shape[0])))
+    n_det = int(min(total, max(threads, rate * target_s / w["src_x"].shape[0])))
     n_det = max(threads, (n_det // threads) * threads)
     rate, dt = time_cpu_sample(w, n_det, threads)
     return {"value": rate, "unit": "terms/s", "cores": threads, "kind": "port",
@@ -169,13 +188,14 @@ def run_reference(args):
     import oracle
     oracle.build()
     threads = host_threads()
-    w = cpu_workload()
-    n_src = w["src_x"].shape[0]
+    w = cpu_workload(args.gpus)
+    n_src, total = w["src_x"].shape[0], w["det_x"].shape[0]
+    tag, K, G = workload(args.gpus)
     time_cpu_sample(w, max(threads, 16), threads)
     rate, _ = time_cpu_sample(w, 4 * max(threads, 16), threads)
     step_s = float(os.environ.get("AKB_BENCH_REF_STEP_S", "4.0"))  # CPU seconds per step (tests shorten it)
     n_det = int(max(threads, rate * step_s / n_src))
-    n_det = min(GRID * GRID, max(threads, (n_det // threads) * threads))
+    n_det = min(total, max(threads, (n_det // threads) * threads))
     for i in range(args.warmup):
         time_cpu_sample(w, n_det, threads, rng_seed=100 + i)
     t = 0.0
@@ -183,38 +203,49 @@ def run_reference(args):
         _, dt = time_cpu_sample(w, n_det, threads, rng_seed=i)
         t += dt
     value = args.steps * n_det * n_src / t
-    sample = (f"per step: {n_det} random detector points of the C3 512x512 grid x all {n_src} source points "
+    sample = (f"per step: {n_det} random detector points of the {tag.upper()} {G}x{G} grid x all {n_src} source points "
               f"({n_det * n_src:.3g} terms), CPU restatement of CPU0402:71-124 (oracle/akb_oracle.c, OpenMP)")
     print(json.dumps({
         "impl": "reference", "metric": "fresnel_terms_per_s", "value": value, "unit": "terms/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": "terms/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def workload_config(n_gpus):
-    name = ("C3: KB two-mirror trace of 1e6 rays + Fresnel sum onto a 512x512 focal grid, 1 GPU" if n_gpus == 1 else
-            f"C3 weak-scaled: 1e6 source points x 512x{512 * n_gpus} focal grid, one 512x512 array_split block per "
-            f"GPU, NCCL all-gather (N=8 is half of C4's 2048x2048 detector)")
-    return {"workload": name, "rays": RAYS * RAYS, "mirrors": 2, "detector_points": GRID * GRID * n_gpus,
-            "terms_per_step": float(RAYS * RAYS) * GRID * GRID * n_gpus, "wavelength_m": WAVELENGTH,
-            "phase_mode": "faithful", "l2": "flushed between timed steps (256 MiB write)"}
-
-
 # ------------------------------------------------------------------------------------ our arm
 
+def sass_costs():
+    """FP64 instruction mix per pair of the loops the default pair kernel runs, read from the loaded library's SASS
+    (tools/sass_cost.py) so that the roofline's instruction counts cannot go stale; None without cuobjdump."""
+    try:
+        from tools import sass_cost
+        from akbraytracing_b200 import _lib
+        return sass_cost.default_kernel_loops(_lib.LIB_PATH)
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
+def ncu_traffic():
+    """dram bytes per launch of the C3 bench launch from this round's committed ncu capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as fh:
+            return json.load(fh)
+    except (OSError, ValueError):
+        return None
+
+
 def run_ours(args):
+    import ctypes
     import torch
     import torch.distributed as dist
     from akbraytracing_b200 import build as akb_build
     akb_build.ensure_built()  # no-op when the in-tree library is current; ranks serialise on a file lock
     import akbraytracing_b200 as akb
     from akbraytracing_b200 import handoff, raytrace, workloads, _lib
-    import ctypes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -237,41 +268,43 @@ def run_ours(args):
             os.dup2(saved, 1)
             os.close(saved)
     L = _lib.load()
+    tag, K, GRID = workload(world)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident inputs
-    coeffs, neg, plane, ray, src = workloads.chain_inputs("c3", RAYS, dev)
+    # ---- resident inputs: ray bundle, full focal grid (every rank holds it, like the reference's x, y, z)
+    coeffs, neg, plane, ray, src = workloads.chain_inputs(tag, RAYS, dev)
     k = 2.0 * np.pi / WAVELENGTH
     tr0 = raytrace.trace_chain(coeffs, neg, plane, ray, src)
-    G_total = GRID * GRID * world
-    # global detector grid: 512 x (512*world); rank r owns the r-th array_split block
-    det = tr0["det"]
-    yc = float((det[1].min() + det[1].max()) / 2); zc = float((det[2].min() + det[2].max()) / 2)
-    yg = torch.linspace(yc - 1e-6, yc + 1e-6, GRID, dtype=torch.float64, device=dev)
-    zg = torch.linspace(zc - 1e-6 * world, zc + 1e-6 * world, GRID * world, dtype=torch.float64, device=dev)
-    zz, yy = torch.meshgrid(zg, yg, indexing="ij")
-    gx = torch.full((G_total,), float(det[0].mean()), dtype=torch.float64, device=dev)
-    gy, gz = yy.reshape(-1).contiguous(), zz.reshape(-1).contiguous()
+    gx, gy, gz = workloads.focal_grid(tr0["det"], GRID)
+    G_total = GRID * GRID
     begin, count = _lib.shard_range(G_total, world, rank)
     sl = slice(begin, begin + count)
-    dx, dy, dz = gx[sl].contiguous(), gy[sl].contiguous(), gz[sl].contiguous()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gathered = torch.empty(G_total, dtype=torch.complex128, device=dev) if world > 1 else None
 
-    def step():
+    def sources():
         tr = raytrace.trace_chain(coeffs, neg, plane, ray, src, check=False)
         last = tr["points"][-1]
-        u = handoff.opl_to_field(tr["dist"][0] + tr["dist"][1], k)
+        opl = tr["dist"][0]
+        for q in range(1, K):
+            opl = opl + tr["dist"][q]
+        u = handoff.opl_to_field(opl, k)
         ds = handoff.calc_dS(last, RAYS, RAYS).reshape(-1)
-        field = akb.fresnel_sum(dx, dy, dz, last[0], last[1], last[2], u, k, ds)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(torch.float64), field.view(torch.float64))
-            return gathered
-        return field
+        return last, u, ds
+
+    def step():
+        last, u, ds = sources()
+        if world > 1:  # the reference-shaped multi-GPU call: full arrays in, full field out on every rank
+            return akb.forward_propagation_cupy_batch_multi_gpu(gx, gy, gz, last[0], last[1], last[2], u, k, ds)
+        return akb.fresnel_sum(gx, gy, gz, last[0], last[1], last[2], u, k, ds)
+
+    # ---- parity before timing (every rank)
+    parity = None
+    if world > 1:
+        parity = multi_gpu_parity(akb, torch, dist, step(), sources, (gx, gy, gz), k, world, rank, dev)
 
     L.akb_fresnel_timing(1)
     for _ in range(args.warmup):
@@ -297,40 +330,43 @@ def run_ours(args):
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     pair_mean = torch.tensor([float(np.mean(pair_ms))], dtype=torch.float64, device=dev)
+    nlaunch = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(pair_mean, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nlaunch, op=dist.ReduceOp.SUM)
     total_ms, pair_mean = float(total_ms.item()), float(pair_mean.item())
     terms_step = float(RAYS * RAYS) * G_total
     value = terms_step * args.steps / (total_ms * 1e-3)
     plan = {"source_splits": sp.value, "detector_blocks": bx.value, "resident_blocks_per_sm": ps.value}
 
-    # ---- end to end through the host-buffer call (H2D + kernels + D2H inside the timed region)
-    tr = raytrace.trace_chain(coeffs, neg, plane, ray, src)
-    last = tr["points"][-1]
-    u = handoff.opl_to_field(tr["dist"][0] + tr["dist"][1], k)
-    ds = handoff.calc_dS(last, RAYS, RAYS).reshape(-1)
+    # ---- end to end through the reference-facing call with HOST buffers (H2D + kernels (+ gather) + D2H timed)
+    last, u, ds = sources()
+    dev_args = [gx, gy, gz, last[0].contiguous(), last[1].contiguous(), last[2].contiguous(), u, ds]
 
-    def pinned(t):
-        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    def host_copy(t, pin):
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=pin)
         h.copy_(t)
         return h.numpy()
-    host = [pinned(t) for t in (dx, dy, dz, last[0].contiguous(), last[1].contiguous(), last[2].contiguous(), u, ds)]
-    h2d = sum(a.nbytes for a in host)
-    d2h = count * 16
-    e2e_steps = max(1, min(args.steps, 3))
-    akb.forward_propagation_numpy_batch(*host[:7], k, host[7])  # warm-up
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        host_out = akb.forward_propagation_numpy_batch(*host[:7], k, host[7])
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = terms_step * e2e_steps / float(e2e_s.item())
-    same = float((torch.as_tensor(host_out).to(dev) - out[sl] if world > 1 else
-                  torch.as_tensor(host_out).to(dev) - out).abs().max())
+    api = akb.forward_propagation_numpy_batch if world == 1 else akb.forward_propagation_cupy_batch_multi_gpu
+
+    def e2e_run(pin, steps):
+        host = [host_copy(t, pin) for t in dev_args]
+        res = api(*host[:7], k, host[7])  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = api(*host[:7], k, host[7])
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return terms_step * steps / float(dt.item()), res, sum(a.nbytes for a in host)
+    e2e_steps = max(1, min(args.steps, 10))
+    e2e_value, host_out, h2d = e2e_run(True, e2e_steps)
+    e2e_pageable, _, _ = e2e_run(False, max(1, min(args.steps, 5)))
+    d2h = G_total * 16
+    same = float((torch.as_tensor(host_out).to(dev) - out).abs().max())
 
     result = None
     if rank == 0:
@@ -338,70 +374,79 @@ def run_ours(args):
         tf = ctypes.c_double()
         _lib.check(L.akb_fp64_peak_probe(4096, ctypes.byref(tf), None), "akb_fp64_peak_probe")
         fp64_peak = tf.value
+        costs = sass_costs()
+        row = (costs or {}).get("planar_row") or {}
+        instr_per_term, exec_flop = row.get("fp64_instr_per_pair"), row.get("exec_flop_per_pair")
         pair_terms = float(RAYS * RAYS) * count
-        achieved = pair_terms * ALG_FLOP_PER_TERM / (pair_mean * 1e-3) / 1e12
+        rate = pair_terms / (pair_mean * 1e-3)
+        achieved = rate * ALG_FLOP_PER_TERM / 1e12
+        traffic = ncu_traffic() if world == 1 else None
         roofline = {
-            "kernel": "fresnel_pairs_kernel<faithful> [%s]" % L.akb_fresnel_variant_name().decode(), "bound": "fp64",
-            "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of THIS launch (1e6 sources x 512x512 detectors,
-            # 15 source splits) from ncu --set full: profiles/r01h_ncu_full_bench_launch.md (57.7 MB + 24.7 MB).
-            # Algorithmic bytes: 48 MB packed sources + 6.3 MB detector xyz + 63 MB partial sums (mostly L2-resident
-            # until the reduction kernel consumes them).
-            "traffic": 82.3e6 if world == 1 else None, "traffic_unit": "bytes per launch (ncu, round 1)",
+            "kernel": "fresnel_pairs_kernel<faithful> [%s], planar-row loop" % L.akb_fresnel_variant_name().decode(),
+            "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+            "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+            "traffic_source": traffic["source"] if traffic else "no ncu capture of this launch committed for this round",
             "peak_source": "on-box DFMA microbenchmark (akb_fp64_peak_probe, measured in this run); "
                            "MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
+            "peak_nominal": 37.2, "frac_of_nominal": achieved / 37.2,
             "algorithmic_flop_per_term": ALG_FLOP_PER_TERM,
-            "executed_flop_per_term": EXEC_FLOP_PER_TERM,
-            "achieved_exec": achieved * EXEC_FLOP_PER_TERM / ALG_FLOP_PER_TERM,
-            "frac_exec": achieved * EXEC_FLOP_PER_TERM / ALG_FLOP_PER_TERM / fp64_peak,
-            # issue-slot view of the same pipe: a DFMA-only stream reaches `peak` with one FP64
-            # instruction per 2 cycles; this kernel issues FP64_INSTR_PER_TERM of them per term
-            "fp64_instr_per_term": FP64_INSTR_PER_TERM,
-            "frac_pipe_issue": (pair_terms / (pair_mean * 1e-3)) * FP64_INSTR_PER_TERM * 2.0 / (fp64_peak * 1e12),
+            "sass": costs,  # instruction mix per pair read from the loaded .so (planar-row and general loop)
+            "executed_flop_per_term": exec_flop, "fp64_instr_per_term": instr_per_term,
+            "achieved_exec": rate * exec_flop / 1e12 if exec_flop else None,
+            "frac_exec": rate * exec_flop / 1e12 / fp64_peak if exec_flop else None,
+            # issue-slot view of the same pipe: a DFMA-only stream reaches `peak` with one FP64 instruction per
+            # 2 cycles; this kernel issues fp64_instr_per_term of them per term
+            "frac_pipe_issue": rate * instr_per_term * 2.0 / (fp64_peak * 1e12) if instr_per_term else None,
             "kernel_ms": pair_mean, "kernel_share_of_step": pair_mean * args.steps / total_ms,
-            "terms_per_s_kernel": pair_terms / (pair_mean * 1e-3), "plan": plan,
+            "terms_per_s_kernel": rate, "plan": plan,
         }
-        # the reference's GPU path (CuPy, restated in torch) on the first detector points of this rank
-        g_out, g_rate, g_ms = gpu0402_restatement(torch, (dx, dy, dz), (last[0].contiguous(), last[1].contiguous(),
+        result = {
+            "metric": "fresnel_terms_per_s", "value": value, "unit": "terms/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(world), "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": "terms/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                    "api": ("forward_propagation_numpy_batch (akb_fresnel_sum_host)" if world == 1 else
+                            "forward_propagation_cupy_batch_multi_gpu with NumPy buffers on every rank "
+                            "(H2D, akb_fresnel_sum_sharded incl. the NCCL all-gather, D2H of the full field)"),
+                    "host_buffers": "pinned", "timer": "host wall clock around the synchronous call, max over ranks",
+                    "steps": e2e_steps, "max_abs_diff_vs_device_path": same,
+                    "pageable": {"value": e2e_pageable, "unit": "terms/s",
+                                 "note": "the same call on ordinary (pageable) NumPy arrays, what a NumPy caller holds"}},
+            "gpu_launches": int(nlaunch.item()), "roofline": roofline,
+        }
+        if parity is not None:
+            result["parity"] = parity
+    if world == 1 and rank == 0:
+        # ---- secondary blocks (N = 1 only): other loops / kernels of the two paths, each with its own roofline
+        ref_field = out
+        result["roofline_m2m"] = bench_m2m(akb, handoff, raytrace, workloads, torch, dev, L, fp64_peak, costs, k)
+        g_out, g_rate, g_ms = gpu0402_restatement(torch, (gx, gy, gz), (last[0].contiguous(), last[1].contiguous(),
                                                   last[2].contiguous()), u, ds, k)
-        g_ref = (out[sl] if world > 1 else out)[:g_out.shape[0]]
-        gpu_baseline = {"value": g_rate, "unit": "terms/s", "n_gpus": 1,
-                        "kind": "restatement of forward_propagation_cupy_batch (GPU0402:64-136) in torch on the same "
-                                "B200; cupy is not installed",
-                        "sample": f"{g_out.shape[0]} detector points x {last.shape[1]} sources in batches of 128 "
-                                  f"({g_ms:.1f} ms, best of 3 passes)",
-                        "rel_l2_vs_fused_kernel": float(torch.linalg.vector_norm(g_out - g_ref) /
-                                                        torch.linalg.vector_norm(g_ref))}
+        result["gpu_baseline"] = {
+            "value": g_rate, "unit": "terms/s", "n_gpus": 1,
+            "kind": "restatement of forward_propagation_cupy_batch (GPU0402:64-136) in torch on the same B200; cupy is not installed",
+            "sample": f"{g_out.shape[0]} detector points x {last.shape[1]} sources in batches of 128 ({g_ms:.1f} ms, best of 3 passes)",
+            "rel_l2_vs_fused_kernel": float(torch.linalg.vector_norm(g_out - ref_field[:g_out.shape[0]]) /
+                                            torch.linalg.vector_norm(ref_field[:g_out.shape[0]]))}
         del g_out
         torch.cuda.empty_cache()
-        # the two non-default phase modes on this rank's block of the same stage (one warm-up, one timed pass each)
-        ref_field = out[sl] if world > 1 else out
         phase_modes = {}
         for mode_name, mode_id in (("exact", akb.PHASE_EXACT), ("referenced", akb.PHASE_REFERENCED)):
             for rep_i in range(2):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                fm = akb.fresnel_sum(dx, dy, dz, last[0], last[1], last[2], u, k, ds, mode=mode_id)
+                fm = akb.fresnel_sum(gx, gy, gz, last[0], last[1], last[2], u, k, ds, mode=mode_id)
                 e1.record()
                 torch.cuda.synchronize()
             phase_modes[mode_name] = {
-                "terms_per_s": float(RAYS * RAYS) * count / (e0.elapsed_time(e1) * 1e-3),
+                "terms_per_s": terms_step / (e0.elapsed_time(e1) * 1e-3),
                 "rel_l2_vs_faithful": float(torch.linalg.vector_norm(fm - ref_field) / torch.linalg.vector_norm(ref_field))}
         del fm
-        # secondary line: the HBM-bound ray kernel at config C2 (1e7 rays, one mirror)
-        ray_roof = bench_ray_c2(akb, workloads, torch, dev, peaks, peak_src)
-        result = {
-            "metric": "fresnel_terms_per_s", "value": value, "unit": "terms/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world), "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": "terms/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "forward_propagation_numpy_batch (akb_fresnel_sum_host), pinned host buffers",
-                    "timer": "host wall clock around the synchronous call, max over ranks",
-                    "steps": e2e_steps, "max_abs_diff_vs_device_path": same},
-            "gpu_launches": int(launches) * world, "roofline": roofline, "roofline_ray": ray_roof,
-            "gpu_baseline": gpu_baseline, "phase_modes": phase_modes,
-        }
+        result["phase_modes"] = phase_modes
+        result["roofline_ray"] = bench_ray_c2(akb, workloads, torch, dev, peaks, peak_src)
+        result["roofline_chain"] = bench_chain(workloads, torch, L, _lib, peaks, peak_src)
+        result["small_call_us"] = bench_small_call(akb, workloads)
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -410,6 +455,92 @@ def run_ours(args):
         print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_parity(akb, torch, dist, field, sources, grid, k, world, rank, dev):
+    """Checks of the multi-GPU call on every rank: (1) the gathered C4 field against the CPU oracle on 256 random
+    detector points (different points on every rank, all 1e6 sources), peak pixel of the sample included;
+    (2) bit-equality of the gathered field across ranks; (3) an uneven case, M = 4096*world + 3 detector points
+    against the first 20000 sources, in full against the oracle.  Returns the `parity` block (max over ranks)."""
+    import oracle
+    oracle.build()
+    gx, gy, gz = grid
+    last, u, ds = sources()
+    threads = max(1, (os.cpu_count() or 8) // world)
+    rng = np.random.default_rng(1000 + rank)
+    sel = np.sort(rng.choice(field.shape[0], 256, replace=False))
+    st = torch.as_tensor(sel, device=dev)
+    h = [t.cpu().numpy() for t in (gx[st], gy[st], gz[st], last[0], last[1], last[2], u, ds)]
+    ref = oracle.fresnel_sum(*h[:7], k, h[7], nthreads=threads)
+    got = field[st].cpu().numpy()
+    rel = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+    peak_same = int(np.argmax(np.abs(got))) == int(np.argmax(np.abs(ref)))
+    # (2) every rank holds the same bits as rank 0
+    mine = field.clone()
+    dist.broadcast(field.view(torch.float64) if field.is_cuda else field, src=0)
+    ranks_equal = bool(torch.equal(mine, field))
+    # (3) uneven shards through the same call
+    M = 4096 * world + 3
+    n_src = 20000
+    got_u = akb.forward_propagation_cupy_batch_multi_gpu(gx[:M], gy[:M], gz[:M], last[0][:n_src], last[1][:n_src],
+                                                         last[2][:n_src], u[:n_src], k, ds[:n_src])
+    hu = [t.cpu().numpy() for t in (gx[:M], gy[:M], gz[:M], last[0][:n_src], last[1][:n_src], last[2][:n_src], u[:n_src], ds[:n_src])]
+    ref_u = oracle.fresnel_sum(*hu[:7], k, hu[7], nthreads=threads)
+    rel_u = float(np.linalg.norm(got_u.cpu().numpy() - ref_u) / np.linalg.norm(ref_u))
+    agg = torch.tensor([rel, rel_u, 0.0 if peak_same else 1.0, 0.0 if ranks_equal else 1.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+    a = agg.cpu().tolist()
+    return {"rel_l2": a[0], "peak_same": a[2] == 0.0, "ranks_equal": a[3] == 0.0, "uneven_rel_l2": a[1],
+            "uneven_case": f"M = {M} detector points over {world} ranks x {n_src} sources, checked in full",
+            "sample": f"256 random detector points per rank x 1e6 sources vs oracle/akb_oracle.c ({threads} host threads per rank); "
+                      f"max over {world} ranks", "gate": 1e-6}
+
+
+def bench_m2m(akb, handoff, raytrace, workloads, torch, dev, L, fp64_peak, costs, k):
+    """The mirror-to-mirror stage of the reference's chain (CPU0402:283-327: N x N terms, three of them per AKB run):
+    detector set = a mirror's traced point cloud (irregular: the pair kernel's GENERAL loop), here the first 262144
+    points of the AKB chain's 2nd mirror against the 1e6 points of its 1st mirror."""
+    import ctypes
+    import oracle
+    coeffs, neg, plane, ray, src = workloads.chain_inputs("c4", RAYS, dev)
+    tr = raytrace.trace_chain(coeffs, neg, plane, ray, src)
+    back, front = tr["points"][0], tr["points"][1][:, :512 * 512].contiguous()
+    u = handoff.opl_to_field(tr["dist"][0], k)
+    ds = handoff.calc_dS(back, RAYS, RAYS).reshape(-1)
+    terms = float(back.shape[1]) * front.shape[1]
+    out = {}
+    fields = {}
+    for name, mode in (("faithful", akb.PHASE_FAITHFUL), ("exact", akb.PHASE_EXACT), ("referenced", akb.PHASE_REFERENCED)):
+        best = None
+        for rep in range(3):
+            f = akb.fresnel_sum(front[0], front[1], front[2], back[0], back[1], back[2], u, k, ds, mode=mode)
+            p, t = ctypes.c_double(), ctypes.c_double()
+            L.akb_fresnel_last_timing(ctypes.byref(p), ctypes.byref(t), None, None, None)
+            if rep:
+                best = p.value if best is None else min(best, p.value)
+        fields[name] = f
+        out[name] = {"kernel_ms": best, "terms_per_s": terms / (best * 1e-3)}
+    sel = np.sort(np.random.default_rng(7).choice(front.shape[1], 64, replace=False))
+    st = torch.as_tensor(sel, device=dev)
+    h = [t.cpu().numpy() for t in (front[0][st], front[1][st], front[2][st], back[0], back[1], back[2], u, ds)]
+    ref = oracle.fresnel_sum(*h[:7], k, h[7])
+    for name in fields:
+        got = fields[name][st].cpu().numpy()
+        out[name]["rel_l2_vs_oracle"] = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+    from akbraytracing_b200.stagechain import auto_phase_mode
+    auto = auto_phase_mode(k, front.cpu().numpy(), back.cpu().numpy())
+    gen = (costs or {}).get("general") or {}
+    rate = out["faithful"]["terms_per_s"]
+    achieved = rate * ALG_FLOP_PER_TERM / 1e12
+    return {"kernel": "fresnel_pairs_kernel<faithful>, general loop (irregular detector set)",
+            "workload": f"AKB mirror 1 (1e6 points) -> first {front.shape[1]} points of mirror 2, {terms:.3g} terms per launch",
+            "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+            "traffic": None, "fp64_instr_per_term": gen.get("fp64_instr_per_pair"),
+            "executed_flop_per_term": gen.get("exec_flop_per_pair"),
+            "frac_exec": rate * gen["exec_flop_per_pair"] / 1e12 / fp64_peak if gen.get("exec_flop_per_pair") else None,
+            "modes": out, "auto_phase_mode": {akb.PHASE_FAITHFUL: "faithful", akb.PHASE_EXACT: "exact"}[auto],
+            "parity_sample": "64 random detector points x 1e6 sources vs oracle/akb_oracle.c",
+            "timing": "CUDA events inside the library around the pair kernel, best of 2 after a warm-up"}
 
 
 def gpu0402_restatement(torch, det, src, u, ds, k, batch=128, batches=4):
@@ -479,14 +610,74 @@ def bench_ray_c2(akb, workloads, torch, dev, peaks, peak_src, n=3163, reps=5):
     cpu_s = time.perf_counter() - t0
     cpu = {"value": n_cpu / cpu_s, "unit": "rays/s", "cores": 1, "kind": "port",
            "sample": f"first {n_cpu} rays of the C2 bundle, oracle/numpy_port.py (NumPy restatement of ER3D:18-71), {cpu_s:.2f} s"}
-    return {"kernel": "intersect_reflect_kernel<2, normal>", "workload": f"C2: {N} rays, single elliptical mirror",
-            "cpu_baseline": cpu,
+    return {"kernel": "intersect_reflect_strided_kernel<2, true> (ell.calc_reflect: points + normal + reflect)",
+            "workload": f"C2: {N} rays, single elliptical mirror", "cpu_baseline": cpu,
             "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
             "traffic": None, "peak_source": peak_src, "bytes_per_ray": bpr, "rays_per_s": N / (ms * 1e-3),
-            "kernel_ms": ms, "without_normal": {"bytes_per_ray": bpr2, "kernel_ms": ms2,
-                                                "achieved": N * bpr2 / (ms2 * 1e-3) / 1e9,
+            "kernel_ms": ms, "without_normal": {"kernel": "intersect_reflect_strided_kernel<2, false>", "bytes_per_ray": bpr2,
+                                                "kernel_ms": ms2, "achieved": N * bpr2 / (ms2 * 1e-3) / 1e9,
                                                 "rays_per_s": N / (ms2 * 1e-3)},
             "timing": "best of 5 after 2 warm-ups, CUDA events; arrays of 240 MB each exceed L2"}
+
+
+def bench_chain(workloads, torch, L, _lib, peaks, peak_src, n=3163, reps=5):
+    """The fused K-mirror chain at 1e7 rays through the C-ABI on preallocated device buffers: K = 2 (KB geometry) and
+    K = 4 (AKB geometry), outputs hit points + last direction + detector point + optical path
+    (48 + 24 K + 24 + 24 + 8 bytes per ray)."""
+    import ctypes
+    out = {}
+    for tag in ("c3", "c4"):
+        coeffs, neg, plane, ray, src = workloads.chain_inputs(tag, n, "cuda")
+        K, N = len(neg), ray.shape[1]
+        co = np.ascontiguousarray(np.asarray(coeffs, dtype=np.float64)); ng = np.ascontiguousarray(np.asarray(neg, dtype=np.int32))
+        pl = np.ascontiguousarray(np.asarray(plane, dtype=np.float64))
+        e = lambda *s: torch.empty(*s, dtype=torch.float64, device="cuda")  # noqa: E731
+        pts, last, det, opl = e(K, 3, N), e(3, N), e(3, N), e(N)
+        flags = torch.empty(4, dtype=torch.int32, device="cuda")
+        p = _lib.dev_ptr
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        best = None
+        for r in range(reps + 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = L.akb_trace_chain(_lib.host_ptr(co), _lib.host_ptr(ng), K, _lib.host_ptr(pl), p(ray), p(src), N, p(pts), None,
+                                   None, p(last), p(det), None, p(opl), 0, p(flags), st)
+            e1.record()
+            torch.cuda.synchronize()
+            _lib.check(rc, "akb_trace_chain")
+            if r >= 2:
+                best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+        bpr = 48 + 24 * K + 24 + 24 + 8
+        gbs = N * bpr / (best * 1e-3) / 1e9
+        out[f"K{K}"] = {"workload": f"{'KB' if K == 2 else 'AKB'} chain, {N} rays, {K} mirrors + plane + optical path",
+                        "bytes_per_ray": bpr, "kernel_ms": best, "achieved": gbs, "frac": gbs / peaks["hbm_gbs"],
+                        "rays_per_s": N / (best * 1e-3), "mirror_hits_per_s": K * N / (best * 1e-3), "misses": int(flags[0])}
+        del pts, last, det, opl, ray, src
+        torch.cuda.empty_cache()
+    k2 = out["K2"]
+    return {"kernel": "trace_chain_kernel<2> (two rays per thread, streaming loads/stores)", "bound": "hbm",
+            "achieved": k2["achieved"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": k2["frac"], "traffic": None,
+            "peak_source": peak_src, "cases": out,
+            "note": "K = 4 does four mirrors' worth of FP64 work (~180 FP64 instructions per mirror hit, bit-exact "
+                    "reference operation order) for 200 B per ray: it runs into the FP64 pipe before HBM",
+            "timing": "best of 5 after 2 warm-ups, CUDA events, C-ABI on preallocated buffers; arrays exceed L2"}
+
+
+def bench_small_call(akb, workloads, reps=30):
+    """BASELINE config C1 (1e4 sources -> 64x64 grid) through the host-buffer call: latency of one call."""
+    c = workloads.c1_patch()
+    args = (c["x"], c["y"], c["z"], c["sx"], c["sy"], c["sz"], c["u"], c["k"], c["ds"])
+    for _ in range(3):
+        akb.forward_propagation_numpy_batch(*args)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        akb.forward_propagation_numpy_batch(*args)
+        ts.append(time.perf_counter() - t0)
+    med = float(np.median(ts))
+    return {"median": med * 1e6, "min": float(min(ts)) * 1e6, "terms_per_s": len(c["x"]) * len(c["sx"]) / med,
+            "workload": "C1: 4096 detector points x 1e4 sources, forward_propagation_numpy_batch with NumPy arrays "
+                        "(one staged H2D copy, pack + pair + reduce kernels, one D2H copy)"}
 
 
 def main():

@@ -40,6 +40,17 @@ def test_reference_arm_is_silent_on_other_ranks():
     assert out.strip() == ""
 
 
+def test_reference_arm_at_n2_times_the_c4_stage():
+    """N > 1 is BASELINE config 4 (AKB trace, fixed 2048x2048 detector, strong scaling): the reference arm samples the
+    same stage, on rank 0 only."""
+    out = _run({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}, "--gpus", "2")
+    d = json.loads([l for l in out.splitlines() if l.strip()][0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["scaling"] == "strong"
+    assert d["config"]["workload"].startswith("C4") and d["config"]["detector_points"] == 2048 * 2048
+    assert d["config"]["mirrors"] == 4 and d["config"]["terms_per_step"] == 1e6 * 2048 * 2048
+    assert "C4 2048x2048" in d["cpu_baseline"]["sample"]
+
+
 import pytest  # noqa: E402
 
 
@@ -65,5 +76,17 @@ def test_our_arm_prints_one_json_line_with_the_contract_keys():
     e = d["e2e"]
     assert e["value"] > 1e11 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     assert e["max_abs_diff_vs_device_path"] == 0.0  # host-buffer call and device call: the same bits
+    assert e["steps"] >= 1 and e["pageable"]["value"] > 1e11
     assert d["gpu_baseline"]["rel_l2_vs_fused_kernel"] < 1e-9
     assert d["roofline_ray"]["bound"] == "hbm" and 0.5 < d["roofline_ray"]["frac"] < 1.0
+    assert "strided" in d["roofline_ray"]["kernel"]
+    # the instruction counts in the roofline come from the loaded library's SASS
+    assert r["fp64_instr_per_term"] == r["sass"]["planar_row"]["fp64_instr_per_pair"] == 25.5
+    m = d["roofline_m2m"]
+    assert m["bound"] == "fp64" and m["fp64_instr_per_term"] == 29.0 and 0.0 < m["frac"] < 1.0
+    for mode in ("faithful", "exact", "referenced"):
+        assert m["modes"][mode]["terms_per_s"] > 1e11
+    assert m["modes"]["faithful"]["rel_l2_vs_oracle"] < 1e-11 and m["modes"]["exact"]["rel_l2_vs_oracle"] < 1e-6
+    c = d["roofline_chain"]
+    assert c["bound"] == "hbm" and c["cases"]["K2"]["misses"] == 0 and c["cases"]["K4"]["misses"] == 0
+    assert 0.3 < c["frac"] < 1.0 and d["small_call_us"]["median"] > 0
