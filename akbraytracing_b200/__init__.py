@@ -10,6 +10,7 @@ from .raytrace import (PlanePoints, ell, intersect_reflect, mirr_ray_intersectio
                        trace_chain_batched, wavefront_opl)
 from .handoff import calc_dS, opl_to_field
 from .psf import compute_psf_fft, field_to_pupil, psf_to_db
+from .throughfocus import compute_psf_fft_batch, fresnel_sum_planes, psf_stack
 from .stagechain import auto_phase_mode, load_handoff, parse_conditions, run_stage_chain, write_handoff
 
 __version__ = "0.2.0"

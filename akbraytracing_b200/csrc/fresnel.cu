@@ -47,10 +47,16 @@ constexpr int HEAD = 4; // per-tile header after the rows: reference point c_T (
 //                 constants |w| and -|w|/2, one DMUL),  a = C - S tan f,  b = S + C tan f  (two DFMA on the
 //                 raw table entry),  acc += W (a, -b)  (two DFMA): 9 instead of 11 FP64 instructions for
 //                 polynomials + rotation + accumulation -- the table entry is never scaled component-wise.
-enum { FORM_TAN = 1, FORM_SHORTCOS = 2, FORM_POLAR = 4, FORM_WFOLD = 8 };
-// rows of a packed source tile: sx, sy, sz, then (w_re, w_im) or (|w|, -frac(arg w), MAGIC - m [, -|w|/2])
-__host__ __device__ constexpr int rows_of(int form) { return (form & FORM_WFOLD) ? 7 : (form & FORM_POLAR) ? 6 : 5; }
-constexpr int MAX_ROWS = 7;
+//   FORM_E2       (REFERENCED, with FORM_WFOLD) an 8th row carries |e_j|^2 of the source's offset e_j from its tile's
+//                 reference point, so that  r^2 - |D|^2 = |e|^2 + e . (-2D)  costs three DFMAs per pair (one on
+//                 planar-row blocks) instead of three DADDs, a DMUL and two DFMAs.
+enum { FORM_TAN = 1, FORM_SHORTCOS = 2, FORM_POLAR = 4, FORM_WFOLD = 8, FORM_E2 = 16 };
+// rows of a packed source tile: sx, sy, sz, then (w_re, w_im) or (|w|, -frac(arg w), MAGIC - m [, -|w|/2 [, |e|^2]])
+__host__ __device__ constexpr int rows_of(int form)
+{
+    return (form & FORM_E2) ? 8 : (form & FORM_WFOLD) ? 7 : (form & FORM_POLAR) ? 6 : 5;
+}
+constexpr int MAX_ROWS = 8;
 
 struct PhaseConst {
     double k;        // FAITHFUL: phase = fl(k * r)
@@ -61,6 +67,10 @@ struct PhaseConst {
     double q_hi;     // EXACT: units per metre, k/u = q_hi + q_lo
     double q_lo;
     double im_sign;  // -1 for k < 0: exp(+i|k|r) = conj(exp(-i|k|r)), evaluated with conjugated weights
+    // Copies of q_hi, q_lo, u for the once-per-(detector, tile) code of REFERENCED mode.  Without them ptxas keeps the
+    // values in vector registers for that code and then feeds the pair loop's DFMAs from those registers: three
+    // register reads per DFMA instead of two plus a uniform operand (+1.75 FP64-pipe cycles each, three per pair).
+    double tq_hi, tq_lo, tu;
 };
 
 // ---------------------------------------------------------------- pack
@@ -88,9 +98,13 @@ __global__ void pack_sources_kernel(const double *__restrict__ sx, const double 
     // (differences of nearby points: exact or within 1e-18 m)
     const long long jc = t_idx * tile < N ? t_idx * tile : N - 1;
     const double cx = sx[jc], cy = sy[jc], cz = sz[jc];
-    t[0 * tile + o] = relative ? sub(sx[jj], cx) : sx[jj];
-    t[1 * tile + o] = relative ? sub(sy[jj], cy) : sy[jj];
-    t[2 * tile + o] = relative ? sub(sz[jj], cz) : sz[jj];
+    const double ex = relative ? sub(sx[jj], cx) : sx[jj];
+    const double ey = relative ? sub(sy[jj], cy) : sy[jj];
+    const double ez = relative ? sub(sz[jj], cz) : sz[jj];
+    t[0 * tile + o] = ex;
+    t[1 * tile + o] = ey;
+    t[2 * tile + o] = ez;
+    if (ROWS > 7) t[7 * tile + o] = relative ? fma_(ex, ex, fma_(ey, ey, mul(ez, ez))) : 0.0; // FORM_E2: |e|^2
     if (polar) {
         // w = |w| e^{i phi},  phi = m u + g  (u = table step, m integer, |g| <= u/2):
         //   w e^{-i p} = |w| e^{-i((p - g) - m u)}  ->  table index n - m, remainder f - g
@@ -238,11 +252,11 @@ __device__ __forceinline__ RefCtx make_ref_ctx(double X, double Y, double Z, dou
     if (r0 > 0.0) rl = __ddiv_rn(sl, 2.0 * r0);
     r.r_ref = r0;
     // k R / u = n_ref + phi with (r0 + rl) * (q_hi + q_lo)
-    const double t0 = fma_(r0, pc.q_hi, magic);
+    const double t0 = fma_(r0, pc.tq_hi, magic);
     const double n0 = add(t0, KC[KC_NEG_MAGIC]);
-    double phi = fma_(r0, pc.q_hi, -n0);
-    phi = fma_(r0, pc.q_lo, phi);
-    phi = fma_(rl, pc.q_hi, phi);
+    double phi = fma_(r0, pc.tq_hi, -n0);
+    phi = fma_(r0, pc.tq_lo, phi);
+    phi = fma_(rl, pc.tq_hi, phi);
     r.phi = phi;
     r.n_ref = __double2loint(t0);
     return r;
@@ -255,7 +269,7 @@ __device__ __forceinline__ void rotate_acc(double &ar, double &ai, const double2
                                            const PhaseConst &pc, double sg)
 {
     const double2 cs = table[m & (TBL - 1)];
-    const double x = mul(dphi, pc.u); // |x| <= 2 pi / TBL
+    const double x = mul(dphi, pc.tu); // |x| <= 2 pi / TBL
     const double z = mul(x, x);
     const double c = fma_(z, fma_(z, 1.0 / 24.0, -0.5), 1.0);                    // next term x^6/720 <= 2e-20
     const double sn = mul(x, fma_(z, fma_(z, 1.0 / 120.0, -1.0 / 6.0), 1.0));    // next term x^7/5040
@@ -283,19 +297,23 @@ __device__ __forceinline__ PairA pair_phase_a_ref_from_ds(const RefCtx &rc, doub
     return a;
 }
 
-// (ex, ey, ez) = source - tile reference; r^2 - |D|^2 = sum_c e_c (e_c - 2 D_c)
-__device__ __forceinline__ PairA pair_phase_a_ref(const RefCtx &rc, double ex, double ey, double ez,
+// (ex, ey, ez) = source - tile reference; r^2 - |D|^2 = sum_c e_c (e_c - 2 D_c) = |e|^2 + e . g,  g = -2 D.
+// E2: |e|^2 comes from the tile (FORM_E2).
+template <bool E2>
+__device__ __forceinline__ PairA pair_phase_a_ref(const RefCtx &rc, double ex, double ey, double ez, double e2,
                                                   const PhaseConst &pc, double magic)
 {
+    if (E2) return pair_phase_a_ref_from_ds(rc, fma_(ex, rc.gx, fma_(ey, rc.gy, fma_(ez, rc.gz, e2))), pc, magic);
     const double ax = add(ex, rc.gx), ay = add(ey, rc.gy), az = add(ez, rc.gz);
     return pair_phase_a_ref_from_ds(rc, fma_(ex, ax, fma_(ey, ay, mul(ez, az))), pc, magic);
 }
 
-// planar-row block: xz = e_x (e_x - 2 D_x) + e_z (e_z - 2 D_z) is shared by the thread's points
+// planar-row block: the x and z terms (E2: and |e|^2) are shared by the thread's points, xz holds them
+template <bool E2>
 __device__ __forceinline__ PairA pair_phase_a_ref_row(const RefCtx &rc, double xz, double ey, const PhaseConst &pc,
                                                       double magic)
 {
-    return pair_phase_a_ref_from_ds(rc, fma_(ey, add(ey, rc.gy), xz), pc, magic);
+    return pair_phase_a_ref_from_ds(rc, E2 ? fma_(ey, rc.gy, xz) : fma_(ey, add(ey, rc.gy), xz), pc, magic);
 }
 
 // r^2 -> (phase, 1/(2r), MAGIC + rint(phase/u))
@@ -438,6 +456,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
     constexpr bool TAN = (FORM & FORM_TAN) != 0;
     constexpr int TILE_DOUBLES = ROWS * TILE + HEAD;
     constexpr bool REF = MODE == AKB_PHASE_REFERENCED;
+    constexpr bool E2 = (FORM & FORM_E2) != 0;
     static_assert(SPI == 1 || SPI == 2, "1 or 2 sources per loop iteration");
     constexpr int NP = SPI * DPT; // pairs per loop iteration: DPT detector points x SPI sources
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -530,10 +549,15 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                     rc[d] = nc;
                 }
             }
-            if (ROW) { // the sx row becomes fl((x0 - sx)^2), CPU0402:76-77 (REFERENCED: e_x (e_x - 2 D_x))
+            if (ROW) { // the sx row becomes fl((x0 - sx)^2), CPU0402:76-77 (REFERENCED: e_x (e_x - 2 D_x);
+                       // FORM_E2: the |e|^2 row becomes |e|^2 + e_x (-2 D_x))
                 for (int q = threadIdx.x; q < TILE; q += THREADS) {
-                    const double ddx = REF ? add(T[q], rc[0].gx) : sub(X[0], T[q]);
-                    T[q] = mul(REF ? T[q] : ddx, ddx);
+                    if (REF && E2) {
+                        T[7 * TILE + q] = fma_(T[q], rc[0].gx, T[7 * TILE + q]);
+                    } else {
+                        const double ddx = REF ? add(T[q], rc[0].gx) : sub(X[0], T[q]);
+                        T[q] = mul(REF ? T[q] : ddx, ddx);
+                    }
                 }
                 // generic-proxy writes to a stage that a later bulk copy (async proxy) overwrites
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -562,6 +586,11 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                 if (ROW) {
 #pragma unroll
                     for (int q = 0; q < SPI; ++q) {
+                        if (REF && E2) { // |e|^2 + e_x g_x (from the tile) + e_z g_z
+                            ddz[q] = 0.0;
+                            dzz[q] = fma_(S[2][q], rc[0].gz, S[7][q]);
+                            continue;
+                        }
                         ddz[q] = REF ? add(S[2][q], rc[0].gz) : sub(Z[0], S[2][q]);
                         dzz[q] = mul(REF ? S[2][q] : ddz[q], ddz[q]);
                         if (REF) dzz[q] = add(S[0][q], dzz[q]); // the x and z terms of r^2 - r_ref^2
@@ -576,9 +605,9 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                     for (int q = 0; q < SPI; ++q) {
                         const int i = SPI * d + q;
                         if (REF && ROW) {
-                            a[i] = pair_phase_a_ref_row(rc[d], dzz[q], S[1][q], pc, S[5][q]);
+                            a[i] = pair_phase_a_ref_row<E2>(rc[d], dzz[q], S[1][q], pc, S[5][q]);
                         } else if (REF) {
-                            a[i] = pair_phase_a_ref(rc[d], S[0][q], S[1][q], S[2][q], pc, S[5][q]);
+                            a[i] = pair_phase_a_ref<E2>(rc[d], S[0][q], S[1][q], S[2][q], S[7][q], pc, S[5][q]);
                         } else if (ROW) {
                             a[i] = pair_phase_a_row<MODE>(S[0][q], Y[d], S[1][q], ddz[q], dzz[q], pc, S[5][q]);
                         } else {
@@ -716,6 +745,9 @@ PhaseConst make_phase_const(double k, int table)
     pc.neg_u_hi = -pi_hi * su;
     pc.neg_u_lo = -pi_lo * su;
     dd_scale(k, ipi_hi * si, ipi_lo * si, pc.q_hi, pc.q_lo);
+    pc.tq_hi = pc.q_hi;
+    pc.tq_lo = pc.q_lo;
+    pc.tu = pc.u;
     return pc;
 }
 
@@ -762,7 +794,7 @@ const KernelEntry *kernel_table(int *count)
         make_entry<2, 256, 3, 2048, 2, FORM_TAN | FORM_POLAR>("dpt2 tile256x3 table2048 tan polar"),
         make_entry<1, 128, 4, 2048, 2, FORM_TAN | FORM_POLAR>("dpt1 tile128x4 table2048 tan polar"),
         // REFERENCED keeps more state per detector point in registers: 2 points per thread
-        make_entry<2, 256, 3, 4096, 2, FORM_DEFAULT>("dpt2 tile256x3 table4096 tan polar shortcos wfold 2 blocks/SM"),
+        make_entry<2, 256, 3, 4096, 2, FORM_DEFAULT | FORM_E2>("dpt2 tile256x3 table4096 tan polar shortcos wfold e2 2 blocks/SM"),
 #ifdef AKB_AB_VARIANTS
         // 4: the round-1 default (scaled table entry, 27.5 / 31 instructions per pair)
         make_entry<4, 256, 3, 4096, 2, FORM_TAN | FORM_POLAR | FORM_SHORTCOS>(
@@ -772,6 +804,9 @@ const KernelEntry *kernel_table(int *count)
         // 6, 7: one source per iteration; 2 points per thread with the default formulation
         make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT, 1>("dpt4 spi1 tile256x3 table4096 wfold"),
         make_entry<8, 256, 3, 4096, 1, FORM_DEFAULT, 1>("dpt8 spi1 tile256x3 table4096 wfold 1 block/SM"),
+        // 8: REFERENCED candidates: 4 points per thread with the |e|^2 row; 9: 2 points without it (round-2 first form)
+        make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT | FORM_E2>("dpt4 tile256x3 table4096 wfold e2 2 blocks/SM"),
+        make_entry<2, 256, 3, 4096, 2, FORM_DEFAULT>("dpt2 tile256x3 table4096 wfold 2 blocks/SM"),
 #endif
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));

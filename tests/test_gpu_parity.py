@@ -662,6 +662,52 @@ def test_chain_opl_and_ray_wave_tail(akb, torch, golden):
         assert np.abs(de2 - w[f"{kind}/DistError2"]).max() <= 1e-3   # 1e-12 m of 146 m: a picometre
 
 
+def test_through_focus_stack_and_batched_psf(akb, torch, golden):
+    """BASELINE config C5 as a product call (4 planes x 128x128 here): fresnel_sum_planes = one launch over the
+    plane-major flat detector set, every block on the planar-row loop; psf_stack = compute_psf_fft per plane with
+    one batched fft2 (vs the single-plane function, and vs the reference's psf_fft golden)."""
+    from akbraytracing_b200 import workloads
+    G, P = 128, 4
+    w = workloads.traced_field_inputs("c3", 200, G, device="cuda")
+    x0 = float(w["det_x"][0])
+    planes = x0 + np.linspace(-1e-3, 1e-3, P)          # defocusForWave = 1e-3 (BIG:89)
+    _row_blocks(akb)
+    stack = akb.fresnel_sum_planes(w["det_y"], w["det_z"], planes, w["src_x"], w["src_y"], w["src_z"], w["u"], w["k"], w["ds"])
+    assert stack.shape == (P, G * G) and stack.is_cuda
+    assert _row_blocks(akb) > 0
+    h = {k: v.cpu().numpy() for k, v in w.items() if k not in ("k", "trace")}
+    rng = np.random.default_rng(9)
+    for p in range(P):
+        one = akb.fresnel_sum(torch.full_like(w["det_y"], planes[p]), w["det_y"], w["det_z"], w["src_x"], w["src_y"], w["src_z"],
+                              w["u"], w["k"], w["ds"])
+        # same arithmetic as a per-plane call; only the split of the source tiles (hence the summation order) differs
+        assert float(torch.linalg.vector_norm(one - stack[p]) / torch.linalg.vector_norm(one)) <= 1e-13
+        sel = np.sort(rng.choice(G * G, 96, replace=False))
+        ref = oracle.fresnel_sum(np.full(96, planes[p]), h["det_y"][sel], h["det_z"][sel], h["src_x"], h["src_y"], h["src_z"],
+                                 h["u"], w["k"], h["ds"])
+        err = rel_l2(stack[p].cpu().numpy()[sel], ref)
+        assert err <= FIELD_TOL and err <= 1e-11, (p, err)
+    # NumPy in -> NumPy out
+    stack_np = akb.fresnel_sum_planes(h["det_y"], h["det_z"], planes[:2], h["src_x"], h["src_y"], h["src_z"], h["u"], w["k"], h["ds"])
+    assert isinstance(stack_np, np.ndarray) and np.array_equal(stack_np, stack[:2].cpu().numpy())
+    # PSF of every plane: batched == one by one
+    pitch = float(w["det_y"][1] - w["det_y"][0])
+    res = akb.psf_stack(stack, (G, G), 13.5e-9, pitch, 0.3, pad_factor=2, planes_per_chunk=3)
+    assert res["planes"] == list(range(P)) and res["I"].shape == (P, 2 * G, 2 * G)
+    for p in range(P):
+        opd, amp = akb.field_to_pupil(stack[p].reshape(G, G), 13.5e-9)
+        I1, x1, y1 = akb.compute_psf_fft(opd, amp, 13.5e-9, pitch, 0.3, pad_factor=2)
+        assert torch.allclose(res["I"][p], I1, rtol=1e-12, atol=1e-18) and torch.equal(res["x"], x1)
+    # the batched function against the reference's own outputs (psf_fft.py run at golden time), as a stack of two
+    g = golden("psf_ref")
+    opd2, amp2 = np.stack([g["opd"], g["opd"] * 0.5]), np.stack([g["amp"], g["amp"]])
+    Ib, xb, yb, Eb = akb.compute_psf_fft_batch(opd2, amp2, 13.5e-9, 1e-4, 0.3, pad_factor=2, return_efield=True)
+    assert np.allclose(Ib[0], g["plain/I"], rtol=1e-10, atol=1e-16) and np.array_equal(xb, g["plain/x"])
+    assert np.allclose(Eb[0], g["plain/E"], rtol=1e-9, atol=1e-15)
+    Ih, _, _ = akb.compute_psf_fft_batch(opd2, amp2, 13.5e-9, 1e-4, 0.3, pad_factor=3, window="hann", pupil_dy_m=1.5e-4)
+    assert np.allclose(Ih[0], g["hann/I"], rtol=1e-10, atol=1e-16)
+
+
 # ------------------------------------------------------------------ production sizes, threads, host ABI
 
 def test_production_sized_surfaces(akb):

@@ -45,3 +45,17 @@ def test_psf_matches_reference_golden_on_cpu_device(golden, tag, kw):
         compute_psf_fft(g["opd"], g["amp"][:-1], 13.5e-9, 1e-4, 0.3, device="cpu")
     with pytest.raises(ValueError):
         compute_psf_fft(g["opd"], g["amp"], 13.5e-9, 1e-4, 0.3, window="hamming", device="cpu")
+
+
+def test_batched_psf_matches_reference_golden_on_cpu_device(golden):
+    """compute_psf_fft_batch (through-focus PSF stack, one batched fft2) against the reference's psf_fft outputs."""
+    from akbraytracing_b200.throughfocus import compute_psf_fft_batch
+    g = golden("psf_ref")
+    opd, amp = np.stack([g["opd"], g["opd"]]), np.stack([g["amp"], g["amp"] * 2.0])
+    I, x, y, E = compute_psf_fft_batch(opd, amp, 13.5e-9, 1e-4, 0.3, pad_factor=2, return_efield=True, device="cpu")
+    assert I.shape[0] == 2 and np.allclose(I[0], g["plain/I"], rtol=1e-10, atol=1e-16)
+    assert np.allclose(I[1], g["plain/I"], rtol=1e-10, atol=1e-16)   # each plane normalised by its own peak
+    assert np.array_equal(x, g["plain/x"]) and np.array_equal(y, g["plain/y"])
+    assert np.allclose(E[0], g["plain/E"], rtol=1e-9, atol=1e-15)
+    with pytest.raises(ValueError):
+        compute_psf_fft_batch(g["opd"], g["amp"], 13.5e-9, 1e-4, 0.3, device="cpu")   # needs (P, ny, nx)

@@ -112,6 +112,19 @@ def _nccl_worker(rank, world, port, out_dir):
             b, n = wavecalc._split(M, world, rank)
             ok = ok and loc.shape[0] == n and torch.equal(loc, dev[b:b + n])
             msgs.append(f"M={M}:{'ok' if ok else 'BAD'}:{rel_l2(got, ref):.2e}")
+        # through-focus stack (config C5): planes x pixels flattened and sharded over the ranks; PSF planes array_split
+        G, P = 32, 3
+        c = _case(G * G, seed=11)
+        planes = 0.15 + np.linspace(-1e-3, 1e-3, P)
+        stack = akb.fresnel_sum_planes(c["y"], c["z"], planes, c["sx"], c["sy"], c["sz"], c["u"], c["k"], c["ds"])
+        ok = isinstance(stack, np.ndarray) and stack.shape == (P, G * G)
+        for p in range(P):
+            ref = oracle.fresnel_sum(np.full(G * G, planes[p]), c["y"], c["z"], c["sx"], c["sy"], c["sz"], c["u"], c["k"], c["ds"], nthreads=2)
+            ok = ok and rel_l2(stack[p], ref) <= 1e-12
+        res = akb.psf_stack(torch.as_tensor(stack).cuda(), (G, G), 13.5e-9, 1e-7, 0.3, pad_factor=2)
+        b, n = wavecalc._split(P, world, rank)
+        ok = ok and res["planes"] == list(range(b, b + n)) and tuple(res["I"].shape) == (n, 2 * G, 2 * G)
+        msgs.append(f"throughfocus:{'ok' if ok else 'BAD'}")
         # a communicator made through the C-ABI instead of PyTorch's
         wavecalc._own_comms.clear()
         os.environ["AKB_OWN_NCCL_COMM"] = "1"
