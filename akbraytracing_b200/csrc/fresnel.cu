@@ -50,7 +50,10 @@ constexpr int HEAD = 4; // per-tile header after the rows: reference point c_T (
 //   FORM_E2       (REFERENCED, with FORM_WFOLD) an 8th row carries |e_j|^2 of the source's offset e_j from its tile's
 //                 reference point, so that  r^2 - |D|^2 = |e|^2 + e . (-2D)  costs three DFMAs per pair (one on
 //                 planar-row blocks) instead of three DADDs, a DMUL and two DFMAs.
-enum { FORM_TAN = 1, FORM_SHORTCOS = 2, FORM_POLAR = 4, FORM_WFOLD = 8, FORM_E2 = 16 };
+//   FORM_SWZ      the table is stored XOR-swizzled, entry m at m ^ ((m >> 3) & 7): a warp whose lanes step through
+//                 the table with an even stride (2, 4, 8 times an odd number) then hits eight different bank
+//                 groups per quarter warp instead of 4, 2 or 1 (A/B variant).
+enum { FORM_TAN = 1, FORM_SHORTCOS = 2, FORM_POLAR = 4, FORM_WFOLD = 8, FORM_E2 = 16, FORM_SWZ = 32 };
 // rows of a packed source tile: sx, sy, sz, then (w_re, w_im) or (|w|, -frac(arg w), MAGIC - m [, -|w|/2 [, |e|^2]])
 __host__ __device__ constexpr int rows_of(int form)
 {
@@ -262,13 +265,25 @@ __device__ __forceinline__ RefCtx make_ref_ctx(double X, double Y, double Z, dou
     return r;
 }
 
+// Table entry (q mod TBL): one LOP3 for the index, then LDS.128 [R.X16 + UR] -- the scaling and the
+// (uniform) table base ride in the load's address mode, so the table needs no alignment.  (An XOR
+// swizzle of the bank-group bits that spreads power-of-two index strides across the lanes was
+// measured twice: 442 vs 449 Gterms/s on C3 in the round-1 kernel, 522.8 vs 521.7 in the present one --
+// the shared-memory pipe is not what limits this kernel.)
+template <int TBL, bool SWZ = false>
+__device__ __forceinline__ double2 table_entry(const double2 *table, int q)
+{
+    if (SWZ) return table[(q ^ ((q >> 3) & 7)) & (TBL - 1)];
+    return table[q & (TBL - 1)];
+}
+
 // acc <- acc * exp(-i (m u + dphi u)):  m whole table steps (any int: the table is periodic in 2^32) and a
 // fraction |dphi| <= 1.  `sg` = +1 when the imaginary accumulator holds -Im (FORM_WFOLD), -1 when it holds +Im.
-template <int TBL>
+template <int TBL, bool SWZ>
 __device__ __forceinline__ void rotate_acc(double &ar, double &ai, const double2 *table, int m, double dphi,
                                            const PhaseConst &pc, double sg)
 {
-    const double2 cs = table[m & (TBL - 1)];
+    const double2 cs = table_entry<TBL, SWZ>(table, m);
     const double x = mul(dphi, pc.tu); // |x| <= 2 pi / TBL
     const double z = mul(x, x);
     const double c = fma_(z, fma_(z, 1.0 / 24.0, -0.5), 1.0);                    // next term x^6/720 <= 2e-20
@@ -355,17 +370,6 @@ __device__ __forceinline__ PairA pair_phase_a_row(double dxx, double Y, double s
     const double s = MODE == AKB_PHASE_FAITHFUL ? add(add(dxx, mul(ddy, ddy)), dzz)
                                                 : fma_(ddz, ddz, fma_(ddy, ddy, dxx));
     return pair_phase_a_from_s<MODE>(s, pc, magic);
-}
-
-// Table entry (q mod TBL): one LOP3 for the index, then LDS.128 [R.X16 + UR] -- the scaling and the
-// (uniform) table base ride in the load's address mode, so the table needs no alignment.  (An XOR
-// swizzle of the bank-group bits that spreads power-of-two index strides across the lanes was
-// measured twice: 442 vs 449 Gterms/s on C3 in the round-1 kernel, 522.8 vs 521.7 in the present one --
-// the shared-memory pipe is not what limits this kernel.)
-template <int TBL>
-__device__ __forceinline__ double2 table_entry(const double2 *table, int q)
-{
-    return table[q & (TBL - 1)];
 }
 
 // exact Cody-Waite reduction + h*(cos f, sin f): n = rint(p/u), f = p - n*u.  fma(n, -u_hi, p) is
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
     for (int m = threadIdx.x; m < TBL; m += THREADS) {
         double sv, cv;
         sincospi((double)m * (2.0 / TBL), &sv, &cv); // exact argument: accurate to < 1 ulp
-        table[m] = make_double2(cv, sv);
+        table[(FORM & FORM_SWZ) ? (m ^ ((m >> 3) & 7)) : m] = make_double2(cv, sv);
     }
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -545,7 +549,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                 for (int d = 0; d < DPT; ++d) {
                     const RefCtx nc = make_ref_ctx(X[d], Y[d], Z[d], T[ROWS * TILE + 0], T[ROWS * TILE + 1],
                                                    T[ROWS * TILE + 2], pc, magic);
-                    if (t > t0) rotate_acc<TBL>(ar[d], ai[d], table, rc[d].n_ref - nc.n_ref, sub(rc[d].phi, nc.phi), pc, SG);
+                    if (t > t0) rotate_acc<TBL, (FORM & FORM_SWZ) != 0>(ar[d], ai[d], table, rc[d].n_ref - nc.n_ref, sub(rc[d].phi, nc.phi), pc, SG);
                     rc[d] = nc;
                 }
             }
@@ -613,7 +617,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                         } else {
                             a[i] = pair_phase_a<MODE>(X[d], Y[d], Z[d], S[0][q], S[1][q], S[2][q], pc, S[5][q]);
                         }
-                        cs[i] = table_entry<TBL>(table, __double2loint(a[i].t));
+                        cs[i] = table_entry<TBL, (FORM & FORM_SWZ) != 0>(table, __double2loint(a[i].t));
                     }
                 }
 #pragma unroll
@@ -683,7 +687,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
         }
         if (REF && t1 > t0) { // out of the last tile's phase frame
 #pragma unroll
-            for (int d = 0; d < DPT; ++d) rotate_acc<TBL>(ar[d], ai[d], table, rc[d].n_ref, rc[d].phi, pc, SG);
+            for (int d = 0; d < DPT; ++d) rotate_acc<TBL, (FORM & FORM_SWZ) != 0>(ar[d], ai[d], table, rc[d].n_ref, rc[d].phi, pc, SG);
         }
     };
     if (row)
@@ -807,6 +811,8 @@ const KernelEntry *kernel_table(int *count)
         // 8: REFERENCED candidates: 4 points per thread with the |e|^2 row; 9: 2 points without it (round-2 first form)
         make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT | FORM_E2>("dpt4 tile256x3 table4096 wfold e2 2 blocks/SM"),
         make_entry<2, 256, 3, 4096, 2, FORM_DEFAULT>("dpt2 tile256x3 table4096 wfold 2 blocks/SM"),
+        // 10: the default with an XOR-swizzled table
+        make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT | FORM_SWZ>("dpt4 tile256x3 table4096 wfold swizzled table"),
 #endif
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));

@@ -689,7 +689,7 @@ def test_through_focus_stack_and_batched_psf(akb, torch, golden):
         assert err <= FIELD_TOL and err <= 1e-11, (p, err)
     # NumPy in -> NumPy out
     stack_np = akb.fresnel_sum_planes(h["det_y"], h["det_z"], planes[:2], h["src_x"], h["src_y"], h["src_z"], h["u"], w["k"], h["ds"])
-    assert isinstance(stack_np, np.ndarray) and np.array_equal(stack_np, stack[:2].cpu().numpy())
+    assert isinstance(stack_np, np.ndarray) and rel_l2(stack_np, stack[:2].cpu().numpy()) <= 1e-13  # (2 planes: another split plan)
     # PSF of every plane: batched == one by one
     pitch = float(w["det_y"][1] - w["det_y"][0])
     res = akb.psf_stack(stack, (G, G), 13.5e-9, pitch, 0.3, pad_factor=2, planes_per_chunk=3)

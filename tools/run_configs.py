@@ -91,10 +91,13 @@ def run_field_config(tag, name, n_rays, G, dev, world, rank, planes=None, n_chec
     M = w["det_x"].shape[0]
     args = (w["det_x"], w["det_y"], w["det_z"], w["src_x"], w["src_y"], w["src_z"], w["u"], w["k"], w["ds"])
 
+    G2 = G * G
+
     def step():
-        if world > 1:
-            return akb.fresnel_sum_sharded(*args)
-        return akb.fresnel_sum(*args)
+        if planes is not None:  # C5 through the product call: planes x pixels flattened, sharded over the ranks
+            return akb.fresnel_sum_planes(w["det_y"][:G2], w["det_z"][:G2], w["det_x"][::G2].contiguous(), w["src_x"], w["src_y"],
+                                          w["src_z"], w["u"], w["k"], w["ds"]).reshape(-1)
+        return akb.forward_propagation_cupy_batch_multi_gpu(*args)  # C4: the reference-shaped multi-GPU call
     step()  # warm-up
     ms, full = timed(step, reps=2 if M * n_rays * n_rays > 1e13 else 3)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -106,18 +109,23 @@ def run_field_config(tag, name, n_rays, G, dev, world, rank, planes=None, n_chec
     if rank == 0:
         err, same_peak = field_subset_parity(w, full, n_check)
         res.update({"rel_l2_vs_oracle_subset": err, "subset": n_check, "subset_peak_pixel_same": same_peak})
-        if psf:  # C5: focal-plane PSF of every plane from the assembled field
-            npl = len(planes)
-            t0 = time.perf_counter()
-            peaks = []
-            for pidx in range(npl):
-                u = full[pidx * G * G:(pidx + 1) * G * G].reshape(G, G)
-                opd, amp = akb.field_to_pupil(u, workloads.WAVELENGTH_EUV)
-                inten, _, _ = akb.compute_psf_fft(opd, amp, workloads.WAVELENGTH_EUV, 2e-6 / (G - 1), 0.1, pad_factor=2)
-                peaks.append(float(inten.max()))
-            torch.cuda.synchronize()
-            res["psf_ms_all_planes"] = (time.perf_counter() - t0) * 1e3
-            res["psf_peaks_all_one"] = bool(all(abs(p - 1.0) < 1e-12 for p in peaks))
+    if psf:  # C5: PSF of every plane from the assembled field, planes array_split over the ranks
+        npl = len(planes)
+        stack = full.reshape(npl, G * G)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = akb.psf_stack(stack, (G, G), workloads.WAVELENGTH_EUV, 2e-6 / (G - 1), 0.1, pad_factor=2)
+        torch.cuda.synchronize()
+        tp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        ok = torch.tensor([1.0 if bool(((out["I"].amax(dim=(-2, -1)) - 1.0).abs() < 1e-12).all()) else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            res["psf_ms_all_planes"] = float(tp.item()) * 1e3
+            res["psf_planes_per_rank"] = len(out["planes"])
+            res["psf_pad_factor"] = 2
+            res["psf_peaks_all_one"] = bool(ok.item() == 1.0)
     return res
 
 
