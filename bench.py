@@ -7,14 +7,14 @@
 One step = one pass of the hot path over one synthetic batch, inputs resident in HBM:
   mirror chain trace of 1000x1000 rays (fused chain kernel) -> calc_dS -> exp(-ik OPL)
   -> Fresnel pair sum of the 1e6 last-mirror points onto the focal grid.
-N = 1: BASELINE config C3 (KB two-mirror trace, 1e6 rays -> 512x512 grid, 2.6e11 terms per step), the largest
-       single-GPU configuration.
-N > 1: BASELINE config C4 as written (AKB four-mirror trace, 1e6 rays x a FIXED 2048x2048 detector = 4.2e12 terms per
-       step, STRONG scaling): every rank passes the full grid to the reference-shaped multi-GPU call
-       forward_propagation_cupy_batch_multi_gpu -> fresnel_sum_sharded -> akb_fresnel_sum_sharded, which computes
-       the rank's array_split block and all-gathers the blocks in place over NCCL.  Before timing, every rank checks
-       the gathered field against the CPU oracle on 256 random detector points, its bit-equality across ranks, and
-       an uneven case (M not divisible by N); the outcome is the `parity` block of the JSON line.
+Every N runs BASELINE config C4 as written -- the configuration the metric "Fresnel terms/s at 1/2/4/8 B200" is quoted
+on: AKB four-mirror trace, 1e6 rays x a FIXED 2048x2048 detector = 4.2e12 terms per step, STRONG scaling.  Every
+rank passes the full grid to the reference-shaped multi-GPU call forward_propagation_cupy_batch_multi_gpu
+(-> fresnel_sum_sharded -> akb_fresnel_sum_sharded for N > 1), which computes the rank's array_split block and
+all-gathers the blocks in place over NCCL.  Before timing, every rank checks the (gathered) field against the CPU
+oracle on 256 random detector points, its bit-equality across ranks, and an uneven case (M not divisible by N); the
+outcome is the `parity` block of the JSON line.  At N = 1 the line also carries C3 (KB two-mirror trace, 1e6 rays ->
+512x512 grid, the round-1 headline) and the rooflines of the other kernels as secondary blocks.
 
 Prints ONE JSON line (rank 0).  `value` = terms of the whole job / max-over-ranks device time.
 `e2e` = the same stage through the reference-facing call with HOST (NumPy) buffers: H2D + kernels (+ all-gather)
@@ -43,14 +43,15 @@ ALG_FLOP_PER_TERM = 23.0   # SURVEY.md 8(d) convention
 
 
 def workload(n_gpus):
-    """(geometry tag, mirrors, focal grid side) of the configuration this run measures."""
-    return ("c3", 2, 512) if n_gpus == 1 else ("c4", 4, 2048)
+    """(geometry tag, mirrors, focal grid side) of the configuration this run measures: C4 at every N."""
+    return ("c4", 4, 2048)
 
 
 def workload_config(n_gpus):
     tag, K, G = workload(n_gpus)
     if n_gpus == 1:
-        name = "C3: KB two-mirror trace of 1e6 rays + Fresnel sum onto a 512x512 focal grid, 1 GPU"
+        name = ("C4: AKB four-mirror trace of 1e6 rays + Fresnel sum onto a fixed 2048x2048 detector, 1 GPU "
+                "(forward_propagation_cupy_batch_multi_gpu on one device)")
     else:
         name = (f"C4: AKB four-mirror trace of 1e6 rays + Fresnel sum onto a fixed 2048x2048 detector, array_split over "
                 f"{n_gpus} GPUs through forward_propagation_cupy_batch_multi_gpu (akb_fresnel_sum_sharded: block kernel + "
@@ -165,7 +166,7 @@ def time_cpu_sample(w, n_det, threads, rng_seed=0):
 
 
 def cpu_baseline(target_s=12.0):
-    """Oracle port (C + OpenMP, all host threads) on a bounded detector subset of the C3 stage."""
+    """Oracle port (C + OpenMP, all host threads) on a bounded detector subset of the C4 stage."""
     import oracle
     oracle.build()
     threads = host_threads()
@@ -177,7 +178,7 @@ def cpu_baseline(target_s=12.0):
     n_det = max(threads, (n_det // threads) * threads)
     rate, dt = time_cpu_sample(w, n_det, threads)
     return {"value": rate, "unit": "terms/s", "cores": threads, "kind": "port",
-            "sample": f"{n_det} random detector points of the C3 grid x all 1e6 source points "
+            "sample": f"{n_det} random detector points of the C4 2048x2048 grid x all 1e6 source points "
                       f"({n_det * w['src_x'].shape[0]:.3g} terms, {dt:.1f} s), oracle/akb_oracle.c with OpenMP"}
 
 
@@ -208,7 +209,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "fresnel_terms_per_s", "value": value, "unit": "terms/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-        "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": "terms/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -229,11 +230,12 @@ def sass_costs():
         return {"error": repr(e)}
 
 
-def ncu_traffic():
-    """dram bytes per launch of the C3 bench launch from this round's committed ncu capture (profiles/), or None."""
+def ncu_traffic(key):
+    """dram bytes per launch of the pair kernel on workload `key` ('c4_n1': the N = 1 bench launch) from this round's
+    committed ncu capture (profiles/r02_ncu_traffic.json), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as fh:
-            return json.load(fh)
+            return json.load(fh).get(key)
     except (OSError, ValueError):
         return None
 
@@ -295,16 +297,20 @@ def run_ours(args):
         ds = handoff.calc_dS(last, RAYS, RAYS).reshape(-1)
         return last, u, ds
 
+    one_device = [local]  # at N = 1 the multi-GPU call is told to stay on this process's device
+
+    def multi(*a):
+        """The reference-shaped multi-GPU call: full arrays in, full field out (on every rank)."""
+        if world > 1:
+            return akb.forward_propagation_cupy_batch_multi_gpu(*a)
+        return akb.forward_propagation_cupy_batch_multi_gpu(*a, devices=one_device)
+
     def step():
         last, u, ds = sources()
-        if world > 1:  # the reference-shaped multi-GPU call: full arrays in, full field out on every rank
-            return akb.forward_propagation_cupy_batch_multi_gpu(gx, gy, gz, last[0], last[1], last[2], u, k, ds)
-        return akb.fresnel_sum(gx, gy, gz, last[0], last[1], last[2], u, k, ds)
+        return multi(gx, gy, gz, last[0], last[1], last[2], u, k, ds)
 
     # ---- parity before timing (every rank)
-    parity = None
-    if world > 1:
-        parity = multi_gpu_parity(akb, torch, dist, step(), sources, (gx, gy, gz), k, world, rank, dev)
+    parity = field_parity(akb, torch, dist, step(), sources, (gx, gy, gz), k, world, rank, dev, multi)
 
     L.akb_fresnel_timing(1)
     for _ in range(args.warmup):
@@ -348,7 +354,7 @@ def run_ours(args):
         h = torch.empty(t.shape, dtype=t.dtype, pin_memory=pin)
         h.copy_(t)
         return h.numpy()
-    api = akb.forward_propagation_numpy_batch if world == 1 else akb.forward_propagation_cupy_batch_multi_gpu
+    api = multi
 
     def e2e_run(pin, steps):
         host = [host_copy(t, pin) for t in dev_args]
@@ -380,7 +386,7 @@ def run_ours(args):
         pair_terms = float(RAYS * RAYS) * count
         rate = pair_terms / (pair_mean * 1e-3)
         achieved = rate * ALG_FLOP_PER_TERM / 1e12
-        traffic = ncu_traffic() if world == 1 else None
+        traffic = ncu_traffic("c4_n1") if world == 1 else None
         roofline = {
             "kernel": "fresnel_pairs_kernel<faithful> [%s], planar-row loop" % L.akb_fresnel_variant_name().decode(),
             "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
@@ -403,10 +409,11 @@ def run_ours(args):
         result = {
             "metric": "fresnel_terms_per_s", "value": value, "unit": "terms/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world), "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "terms/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "api": ("forward_propagation_numpy_batch (akb_fresnel_sum_host)" if world == 1 else
+                    "api": ("forward_propagation_cupy_batch_multi_gpu with NumPy buffers (one device: akb_fresnel_sum_host, "
+                            "H2D + kernels + D2H)" if world == 1 else
                             "forward_propagation_cupy_batch_multi_gpu with NumPy buffers on every rank "
                             "(H2D, akb_fresnel_sum_sharded incl. the NCCL all-gather, D2H of the full field)"),
                     "host_buffers": "pinned", "timer": "host wall clock around the synchronous call, max over ranks",
@@ -415,11 +422,11 @@ def run_ours(args):
                                  "note": "the same call on ordinary (pageable) NumPy arrays, what a NumPy caller holds"}},
             "gpu_launches": int(nlaunch.item()), "roofline": roofline,
         }
-        if parity is not None:
-            result["parity"] = parity
+        result["parity"] = parity
     if world == 1 and rank == 0:
         # ---- secondary blocks (N = 1 only): other loops / kernels of the two paths, each with its own roofline
         ref_field = out
+        result["c3"] = bench_c3(akb, handoff, raytrace, workloads, torch, dev, L, k)
         result["roofline_m2m"] = bench_m2m(akb, handoff, raytrace, workloads, torch, dev, L, fp64_peak, costs, k)
         g_out, g_rate, g_ms = gpu0402_restatement(torch, (gx, gy, gz), (last[0].contiguous(), last[1].contiguous(),
                                                   last[2].contiguous()), u, ds, k)
@@ -433,16 +440,13 @@ def run_ours(args):
         torch.cuda.empty_cache()
         phase_modes = {}
         for mode_name, mode_id in (("exact", akb.PHASE_EXACT), ("referenced", akb.PHASE_REFERENCED)):
-            for rep_i in range(2):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                fm = akb.fresnel_sum(gx, gy, gz, last[0], last[1], last[2], u, k, ds, mode=mode_id)
-                e1.record()
-                torch.cuda.synchronize()
+            fm = akb.fresnel_sum(gx, gy, gz, last[0], last[1], last[2], u, k, ds, mode=mode_id)  # one pass: no warm-up needed at 7 s
+            p_ms = ctypes.c_double()
+            L.akb_fresnel_last_timing(ctypes.byref(p_ms), None, None, None, None)
             phase_modes[mode_name] = {
-                "terms_per_s": terms_step / (e0.elapsed_time(e1) * 1e-3),
+                "terms_per_s": terms_step / (p_ms.value * 1e-3),
                 "rel_l2_vs_faithful": float(torch.linalg.vector_norm(fm - ref_field) / torch.linalg.vector_norm(ref_field))}
-        del fm
+            del fm
         result["phase_modes"] = phase_modes
         result["roofline_ray"] = bench_ray_c2(akb, workloads, torch, dev, peaks, peak_src)
         result["roofline_chain"] = bench_chain(workloads, torch, L, _lib, peaks, peak_src)
@@ -457,8 +461,8 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def multi_gpu_parity(akb, torch, dist, field, sources, grid, k, world, rank, dev):
-    """Checks of the multi-GPU call on every rank: (1) the gathered C4 field against the CPU oracle on 256 random
+def field_parity(akb, torch, dist, field, sources, grid, k, world, rank, dev, multi):
+    """Checks of the timed call on every rank: (1) the (gathered) C4 field against the CPU oracle on 256 random
     detector points (different points on every rank, all 1e6 sources), peak pixel of the sample included;
     (2) bit-equality of the gathered field across ranks; (3) an uneven case, M = 4096*world + 3 detector points
     against the first 20000 sources, in full against the oracle.  Returns the `parity` block (max over ranks)."""
@@ -476,24 +480,68 @@ def multi_gpu_parity(akb, torch, dist, field, sources, grid, k, world, rank, dev
     rel = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
     peak_same = int(np.argmax(np.abs(got))) == int(np.argmax(np.abs(ref)))
     # (2) every rank holds the same bits as rank 0
-    mine = field.clone()
-    dist.broadcast(field.view(torch.float64) if field.is_cuda else field, src=0)
-    ranks_equal = bool(torch.equal(mine, field))
+    ranks_equal = True
+    if world > 1:
+        mine = field.clone()
+        dist.broadcast(field.view(torch.float64) if field.is_cuda else field, src=0)
+        ranks_equal = bool(torch.equal(mine, field))
+        del mine
     # (3) uneven shards through the same call
     M = 4096 * world + 3
     n_src = 20000
-    got_u = akb.forward_propagation_cupy_batch_multi_gpu(gx[:M], gy[:M], gz[:M], last[0][:n_src], last[1][:n_src],
-                                                         last[2][:n_src], u[:n_src], k, ds[:n_src])
+    got_u = multi(gx[:M], gy[:M], gz[:M], last[0][:n_src], last[1][:n_src], last[2][:n_src], u[:n_src], k, ds[:n_src])
     hu = [t.cpu().numpy() for t in (gx[:M], gy[:M], gz[:M], last[0][:n_src], last[1][:n_src], last[2][:n_src], u[:n_src], ds[:n_src])]
     ref_u = oracle.fresnel_sum(*hu[:7], k, hu[7], nthreads=threads)
     rel_u = float(np.linalg.norm(got_u.cpu().numpy() - ref_u) / np.linalg.norm(ref_u))
     agg = torch.tensor([rel, rel_u, 0.0 if peak_same else 1.0, 0.0 if ranks_equal else 1.0], dtype=torch.float64, device=dev)
-    dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
     a = agg.cpu().tolist()
-    return {"rel_l2": a[0], "peak_same": a[2] == 0.0, "ranks_equal": a[3] == 0.0, "uneven_rel_l2": a[1],
+    return {"rel_l2": a[0], "peak_same": a[2] == 0.0, "ranks_equal": a[3] == 0.0 if world > 1 else None, "uneven_rel_l2": a[1],
             "uneven_case": f"M = {M} detector points over {world} ranks x {n_src} sources, checked in full",
             "sample": f"256 random detector points per rank x 1e6 sources vs oracle/akb_oracle.c ({threads} host threads per rank); "
                       f"max over {world} ranks", "gate": 1e-6}
+
+
+def bench_c3(akb, handoff, raytrace, workloads, torch, dev, L, k, G=512):
+    """BASELINE config C3 (KB two-mirror trace of 1e6 rays -> 512x512 focal grid, 2.6e11 terms): the round-1 headline,
+    one warm-up + best of 3 of the whole stage (trace, calc_dS, exp(-ik OPL), pair sum), oracle parity on 64 points."""
+    import ctypes
+    import oracle
+    coeffs, neg, plane, ray, src = workloads.chain_inputs("c3", RAYS, dev)
+    tr0 = raytrace.trace_chain(coeffs, neg, plane, ray, src)
+    gx, gy, gz = workloads.focal_grid(tr0["det"], G)
+
+    def stage():
+        tr = raytrace.trace_chain(coeffs, neg, plane, ray, src, check=False)
+        last = tr["points"][-1]
+        u = handoff.opl_to_field(tr["dist"][0] + tr["dist"][1], k)
+        ds = handoff.calc_dS(last, RAYS, RAYS).reshape(-1)
+        return akb.fresnel_sum(gx, gy, gz, last[0], last[1], last[2], u, k, ds), (last, u, ds)
+    best, best_pair = None, None
+    for rep in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        field, (last, u, ds) = stage()
+        e1.record()
+        torch.cuda.synchronize()
+        p = ctypes.c_double()
+        L.akb_fresnel_last_timing(ctypes.byref(p), None, None, None, None)
+        if rep:
+            best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+            best_pair = p.value if best_pair is None else min(best_pair, p.value)
+    terms = float(RAYS * RAYS) * G * G
+    sel = np.sort(np.random.default_rng(3).choice(G * G, 64, replace=False))
+    st = torch.as_tensor(sel, device=dev)
+    h = [t.cpu().numpy() for t in (gx[st], gy[st], gz[st], last[0], last[1], last[2], u, ds)]
+    ref = oracle.fresnel_sum(*h[:7], k, h[7])
+    got = field[st].cpu().numpy()
+    return {"workload": "C3: KB two-mirror trace of 1e6 rays + Fresnel sum onto a 512x512 focal grid, 1 GPU",
+            "terms_per_step": terms, "ms_per_step": best, "terms_per_s": terms / (best * 1e-3),
+            "pair_kernel_ms": best_pair, "terms_per_s_kernel": terms / (best_pair * 1e-3),
+            "rel_l2_vs_oracle": float(np.linalg.norm(got - ref) / np.linalg.norm(ref)),
+            "parity_sample": "64 random detector points x 1e6 sources vs oracle/akb_oracle.c",
+            "timing": "CUDA events around the whole stage, best of 3 after a warm-up"}
 
 
 def bench_m2m(akb, handoff, raytrace, workloads, torch, dev, L, fp64_peak, costs, k):
@@ -622,8 +670,9 @@ def bench_ray_c2(akb, workloads, torch, dev, peaks, peak_src, n=3163, reps=5):
 
 def bench_chain(workloads, torch, L, _lib, peaks, peak_src, n=3163, reps=5):
     """The fused K-mirror chain at 1e7 rays through the C-ABI on preallocated device buffers: K = 2 (KB geometry) and
-    K = 4 (AKB geometry), outputs hit points + last direction + detector point + optical path
-    (48 + 24 K + 24 + 24 + 8 bytes per ray)."""
+    K = 4 (AKB geometry).  Outputs: hit points + last direction + detector point + the K segment lengths (what
+    trace_chain returns by default and the Fresnel step consumes: SURVEY 8d, 48 + 24 K + 24 + 24 + 8 K bytes per ray), and
+    the same with the summed optical path instead of the segments (+ 8 bytes per ray)."""
     import ctypes
     out = {}
     for tag in ("c3", "c4"):
@@ -632,34 +681,38 @@ def bench_chain(workloads, torch, L, _lib, peaks, peak_src, n=3163, reps=5):
         co = np.ascontiguousarray(np.asarray(coeffs, dtype=np.float64)); ng = np.ascontiguousarray(np.asarray(neg, dtype=np.int32))
         pl = np.ascontiguousarray(np.asarray(plane, dtype=np.float64))
         e = lambda *s: torch.empty(*s, dtype=torch.float64, device="cuda")  # noqa: E731
-        pts, last, det, opl = e(K, 3, N), e(3, N), e(3, N), e(N)
+        pts, last, det, dist, opl = e(K, 3, N), e(3, N), e(3, N), e(K, N), e(N)
         flags = torch.empty(4, dtype=torch.int32, device="cuda")
         p = _lib.dev_ptr
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        best = None
-        for r in range(reps + 2):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            rc = L.akb_trace_chain(_lib.host_ptr(co), _lib.host_ptr(ng), K, _lib.host_ptr(pl), p(ray), p(src), N, p(pts), None,
-                                   None, p(last), p(det), None, p(opl), 0, p(flags), st)
-            e1.record()
-            torch.cuda.synchronize()
-            _lib.check(rc, "akb_trace_chain")
-            if r >= 2:
-                best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
-        bpr = 48 + 24 * K + 24 + 24 + 8
-        gbs = N * bpr / (best * 1e-3) / 1e9
-        out[f"K{K}"] = {"workload": f"{'KB' if K == 2 else 'AKB'} chain, {N} rays, {K} mirrors + plane + optical path",
-                        "bytes_per_ray": bpr, "kernel_ms": best, "achieved": gbs, "frac": gbs / peaks["hbm_gbs"],
-                        "rays_per_s": N / (best * 1e-3), "mirror_hits_per_s": K * N / (best * 1e-3), "misses": int(flags[0])}
-        del pts, last, det, opl, ray, src
+        for form, d_ptr, o_ptr, extra in (("segments", p(dist), None, 8 * K), ("opl", None, p(opl), 8)):
+            best = None
+            for r in range(reps + 2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = L.akb_trace_chain(_lib.host_ptr(co), _lib.host_ptr(ng), K, _lib.host_ptr(pl), p(ray), p(src), N, p(pts), None,
+                                       None, p(last), p(det), d_ptr, o_ptr, 0, p(flags), st)
+                e1.record()
+                torch.cuda.synchronize()
+                _lib.check(rc, "akb_trace_chain")
+                if r >= 2:
+                    best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+            bpr = 48 + 24 * K + 24 + 24 + extra
+            gbs = N * bpr / (best * 1e-3) / 1e9
+            out[f"K{K}_{form}"] = {
+                "workload": f"{'KB' if K == 2 else 'AKB'} chain, {N} rays, {K} mirrors + plane + "
+                            f"{'segment lengths' if form == 'segments' else 'optical path'}",
+                "bytes_per_ray": bpr, "kernel_ms": best, "achieved": gbs, "frac": gbs / peaks["hbm_gbs"],
+                "rays_per_s": N / (best * 1e-3), "mirror_hits_per_s": K * N / (best * 1e-3), "misses": int(flags[0])}
+        del pts, last, det, dist, opl, ray, src
         torch.cuda.empty_cache()
-    k2 = out["K2"]
-    return {"kernel": "trace_chain_kernel<2> (two rays per thread, streaming loads/stores)", "bound": "hbm",
+    k2 = out["K2_segments"]
+    return {"kernel": "trace_chain_kernel<1, 4> (one ray per thread, 4 resident blocks/SM, streaming loads/stores)", "bound": "hbm",
             "achieved": k2["achieved"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": k2["frac"], "traffic": None,
             "peak_source": peak_src, "cases": out,
-            "note": "K = 4 does four mirrors' worth of FP64 work (~180 FP64 instructions per mirror hit, bit-exact "
-                    "reference operation order) for 200 B per ray: it runs into the FP64 pipe before HBM",
+            "note": "headline = K2_segments.  K = 4 does four mirrors' worth of FP64 work (~180 FP64 instructions per mirror "
+                    "hit, bit-exact reference operation order) for 200-224 B per ray: it runs into the FP64 pipe and its "
+                    "latencies before HBM (ncu: profiles/r02d_ncu_full_chain_kernel.md)",
             "timing": "best of 5 after 2 warm-ups, CUDA events, C-ABI on preallocated buffers; arrays exceed L2"}
 
 

@@ -26,7 +26,7 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["metric"] == "fresnel_terms_per_s" and d["unit"] == "terms/s"
     assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["vs_baseline"] is None and d["n_gpus"] == 1
     assert d["steps"] == 1 and d["warmup"] == 3 and d["value"] > 0 and d["ms_per_step"] > 0
-    assert d["config"]["workload"].startswith("C3") and "model" not in d["config"]
+    assert d["config"]["workload"].startswith("C4") and "model" not in d["config"] and d["scaling"] == "strong"
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["unit"] == "terms/s" and cb["sample"]
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
@@ -41,7 +41,7 @@ def test_reference_arm_is_silent_on_other_ranks():
 
 
 def test_reference_arm_at_n2_times_the_c4_stage():
-    """N > 1 is BASELINE config 4 (AKB trace, fixed 2048x2048 detector, strong scaling): the reference arm samples the
+    """Every N is BASELINE config 4 (AKB trace, fixed 2048x2048 detector, strong scaling): the reference arm samples the
     same stage, on rank 0 only."""
     out = _run({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}, "--gpus", "2")
     d = json.loads([l for l in out.splitlines() if l.strip()][0])
@@ -66,7 +66,11 @@ def test_our_arm_prints_one_json_line_with_the_contract_keys():
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
         assert key in d, key
-    assert d["metric"] == "fresnel_terms_per_s" and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["dtype"] == "f64"
+    assert d["metric"] == "fresnel_terms_per_s" and d["n_gpus"] == 1 and d["scaling"] == "strong" and d["dtype"] == "f64"
+    assert d["config"]["workload"].startswith("C4") and d["config"]["terms_per_step"] == 1e6 * 2048 * 2048
+    p = d["parity"]
+    assert p["rel_l2"] < 1e-11 and p["uneven_rel_l2"] < 1e-11 and p["peak_same"] is True and p["ranks_equal"] is None
+    assert d["c3"]["terms_per_s"] > 1e11 and d["c3"]["rel_l2_vs_oracle"] < 1e-11
     assert d["value"] > 1e11 and d["gpu_launches"] > 0  # the CUDA path ran (a CPU fallback could not reach 1e11 terms/s)
     r = d["roofline"]
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
@@ -88,5 +92,5 @@ def test_our_arm_prints_one_json_line_with_the_contract_keys():
         assert m["modes"][mode]["terms_per_s"] > 1e11
     assert m["modes"]["faithful"]["rel_l2_vs_oracle"] < 1e-11 and m["modes"]["exact"]["rel_l2_vs_oracle"] < 1e-6
     c = d["roofline_chain"]
-    assert c["bound"] == "hbm" and c["cases"]["K2"]["misses"] == 0 and c["cases"]["K4"]["misses"] == 0
+    assert c["bound"] == "hbm" and c["cases"]["K2_segments"]["misses"] == 0 and c["cases"]["K4_opl"]["misses"] == 0
     assert 0.3 < c["frac"] < 1.0 and d["small_call_us"]["median"] > 0

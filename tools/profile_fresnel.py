@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small driver for ncu: ONE Fresnel stage (1e6 traced source points -> G x G grid) and one C2-sized
-ray launch.  Usage: python tools/profile_fresnel.py [G] [mode]"""
+ray launch.  Usage: python tools/profile_fresnel.py [G] [mode] [c3|c4]"""
 import os
 import sys
 
@@ -12,7 +12,8 @@ from akbraytracing_b200 import workloads  # noqa: E402
 
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 mode = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-w = workloads.traced_field_inputs("c3", 1000, G, device="cuda")
+tag = sys.argv[3] if len(sys.argv) > 3 else "c3"
+w = workloads.traced_field_inputs(tag, 1000, G, device="cuda")
 for _ in range(2):
     out = akb.fresnel_sum(w["det_x"], w["det_y"], w["det_z"], w["src_x"], w["src_y"], w["src_z"], w["u"], w["k"],
                           w["ds"], mode=mode)
