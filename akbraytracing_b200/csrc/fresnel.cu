@@ -53,7 +53,13 @@ constexpr int HEAD = 4; // per-tile header after the rows: reference point c_T (
 //   FORM_SWZ      the table is stored XOR-swizzled, entry m at m ^ ((m >> 3) & 7): a warp whose lanes step through
 //                 the table with an even stride (2, 4, 8 times an odd number) then hits eight different bank
 //                 groups per quarter warp instead of 4, 2 or 1 (A/B variant).
-enum { FORM_TAN = 1, FORM_SHORTCOS = 2, FORM_POLAR = 4, FORM_WFOLD = 8, FORM_E2 = 16, FORM_SWZ = 32 };
+//   FORM_ROWT     (REFERENCED, with FORM_E2, 4 points per thread) on planar-row blocks only the thread's FIRST point
+//                 takes the square root; its three neighbours in the row, a few nanometres away, get their path
+//                 difference from the expansion of r along the row,  r(y0 + D) - r(y0) = a D + b D^2  with
+//                 a = (y0 - Y_j)/r,  b = (1 - a^2)/(2 r)  (third order: |a| D^3/(2 r^2), guarded below 1e-11 rad
+//                 per block from the bounding box of the source set), and 1/(2r) to first order: 3 DFMAs instead
+//                 of 10 instructions per pair for three pairs out of four.
+enum { FORM_TAN = 1, FORM_SHORTCOS = 2, FORM_POLAR = 4, FORM_WFOLD = 8, FORM_E2 = 16, FORM_SWZ = 32, FORM_ROWT = 64 };
 // rows of a packed source tile: sx, sy, sz, then (w_re, w_im) or (|w|, -frac(arg w), MAGIC - m [, -|w|/2 [, |e|^2]])
 __host__ __device__ constexpr int rows_of(int form)
 {
@@ -76,13 +82,44 @@ struct PhaseConst {
     double tq_hi, tq_lo, tu;
 };
 
+// order-preserving map double -> unsigned 64-bit (for atomicMin / atomicMax on coordinates) and back
+__device__ __forceinline__ unsigned long long dkey(double v)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k)
+{
+    return __longlong_as_double((long long)(k ^ ((k >> 63) ? 0x8000000000000000ull : ~0ull)));
+}
+
 // ---------------------------------------------------------------- pack
 __global__ void pack_sources_kernel(const double *__restrict__ sx, const double *__restrict__ sy,
                                     const double *__restrict__ sz, const double *__restrict__ u,
                                     const double *__restrict__ ds, long long N, long long padded, int tile,
                                     int relative, int polar, int ROWS, double im_sign, double inv_u, double neg_u_hi, double neg_u_lo,
-                                    double *__restrict__ packed)
+                                    double *__restrict__ packed, unsigned long long *__restrict__ bbox)
 {
+    if (bbox) { // bounding box of the source set as order-preserving integer keys: min x,y,z | max x,y,z (FORM_ROWT)
+        const long long jb = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const long long jc = jb < N ? jb : N - 1;
+        unsigned long long kx = dkey(sx[jc]), ky = dkey(sy[jc]), kz = dkey(sz[jc]);
+        unsigned long long mn[3] = {kx, ky, kz}, mx[3] = {kx, ky, kz};
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn[c], o), b = __shfl_xor_sync(0xffffffffu, mx[c], o);
+                mn[c] = a < mn[c] ? a : mn[c];
+                mx[c] = b > mx[c] ? b : mx[c];
+            }
+        if ((threadIdx.x & 31) == 0)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                atomicMin(&bbox[c], mn[c]);
+                atomicMax(&bbox[3 + c], mx[c]);
+            }
+    }
     long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= padded) return;
     long long jj = j < N ? j : N - 1; // padding repeats the last point (finite r) with zero weight
@@ -461,6 +498,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
     constexpr int TILE_DOUBLES = ROWS * TILE + HEAD;
     constexpr bool REF = MODE == AKB_PHASE_REFERENCED;
     constexpr bool E2 = (FORM & FORM_E2) != 0;
+    constexpr bool ROWT = REF && (FORM & FORM_ROWT) != 0;
+    static_assert(!(FORM & FORM_ROWT) || (E2 && DPT >= 2), "FORM_ROWT builds on FORM_E2 and several points per thread");
     static_assert(SPI == 1 || SPI == 2, "1 or 2 sources per loop iteration");
     constexpr int NP = SPI * DPT; // pairs per loop iteration: DPT detector points x SPI sources
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -500,6 +539,24 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
 #pragma unroll
         for (int d = 0; d < DPT; ++d) mine = mine && X[d] == x0 && Z[d] == Z[0];
         row = __syncthreads_and(mine);
+        if (ROWT && row) {
+            // FORM_ROWT expands r along the thread's row about its first point: allowed when the third-order term
+            // |a| D^3 / (2 r^2) stays below 1e-11 rad for every source, r bounded below by the distance from the point
+            // to the bounding box of the source set (left behind the packed tiles by the pack kernel)
+            const unsigned long long *bb = reinterpret_cast<const unsigned long long *>(packed + (long long)tiles_total * TILE_DOUBLES);
+            double r2 = 0.0, dmax = 0.0;
+            const double P0[3] = {X[0], Y[0], Z[0]};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double lo = dunkey(bb[c]), hi = dunkey(bb[3 + c]);
+                const double gap = fmax(fmax(lo - P0[c], P0[c] - hi), 0.0);
+                r2 = fma_(gap, gap, r2);
+            }
+#pragma unroll
+            for (int d = 1; d < DPT; ++d) dmax = fmax(dmax, fabs(sub(Y[d], Y[0])));
+            const bool ok = r2 > 0.0 && pc.k * dmax * dmax * dmax <= 2.0e-11 * r2 && dmax * dmax <= 1.0e-8 * r2;
+            row = __syncthreads_and(ok); // else: the general loop (every point takes its own square root)
+        }
         if (row && threadIdx.x == 0) atomicAdd(&g_row_blocks, 1ULL);
     }
 
@@ -538,12 +595,24 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
         uint32_t parity = 0;
         RefCtx rc[REF ? DPT : 1]; // REFERENCED: the phase frame (tile reference) the accumulators live in
         constexpr double SG = (FORM & FORM_WFOLD) ? 1.0 : -1.0;
+        constexpr bool RT = ROWT && ROW; // only the thread's first point carries a reference context / takes the root
+        double dlt[DPT];                 // RT: offsets of the thread's points from its first one along the row
+#pragma unroll
+        for (int d = 0; d < DPT; ++d) dlt[d] = RT ? sub(Y[d], Y[0]) : 0.0;
         for (int t = t0; t < t1; ++t) {
             mbar_wait(bars_s + 8 * stage, parity);
             double *T = tiles + stage * TILE_DOUBLES;
             const long long left = n_padded - (long long)t * TILE;
             const int cnt = left < TILE ? (int)left : TILE; // multiple of 2
-            if (REF) { // once per (detector point, tile): double-double distance to the tile's reference point,
+            if (RT) { // one context per thread: all its accumulators live in the phase frame of its first point
+                const RefCtx nc = make_ref_ctx(X[0], Y[0], Z[0], T[ROWS * TILE + 0], T[ROWS * TILE + 1], T[ROWS * TILE + 2], pc, magic);
+                if (t > t0) {
+#pragma unroll
+                    for (int d = 0; d < DPT; ++d)
+                        rotate_acc<TBL, (FORM & FORM_SWZ) != 0>(ar[d], ai[d], table, rc[0].n_ref - nc.n_ref, sub(rc[0].phi, nc.phi), pc, SG);
+                }
+                rc[0] = nc;
+            } else if (REF) { // once per (detector point, tile): double-double distance to the tile's reference point,
                        // and the accumulated field moves from the previous tile's phase frame into this one
 #pragma unroll
                 for (int d = 0; d < DPT; ++d) {
@@ -603,12 +672,23 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                 PairA a[NP];
                 double2 cs[NP];
                 double cf[NP], sf[NP];
+                double rta[SPI], rtb[SPI], rtm[SPI]; // RT: dr/dy, (d2r/dy2)/2 and d(1/2r)/dy at the thread's first point
 #pragma unroll
                 for (int d = 0; d < DPT; ++d) {
 #pragma unroll
                     for (int q = 0; q < SPI; ++q) {
                         const int i = SPI * d + q;
-                        if (REF && ROW) {
+                        if (RT && d > 0) {
+                            if (d == 1) { // from the first point's pair: w = y0 - Y_j = -(g_y/2 + e_y), h = 1/(2r)
+                                const double h = a[q].h;
+                                rta[q] = mul(-fma_(2.0, S[1][q], rc[0].gy), h);          // a = 2 w h = w / r
+                                rtb[q] = mul(fma_(-rta[q], rta[q], 1.0), h);            // b = (1 - a^2) / (2r)
+                                rtm[q] = mul(mul(rta[q], h), mul(-2.0, h));             // d(1/2r)/dy = -a / (2 r^2)
+                            }
+                            a[i].p = fma_(dlt[d], fma_(rtb[q], dlt[d], rta[q]), a[q].p);  // r - R
+                            a[i].h = fma_(rtm[q], dlt[d], a[q].h);
+                            a[i].t = fma_(a[i].p, pc.q_hi, S[5][q]);
+                        } else if (REF && ROW) {
                             a[i] = pair_phase_a_ref_row<E2>(rc[d], dzz[q], S[1][q], pc, S[5][q]);
                         } else if (REF) {
                             a[i] = pair_phase_a_ref<E2>(rc[d], S[0][q], S[1][q], S[2][q], S[7][q], pc, S[5][q]);
@@ -687,7 +767,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
         }
         if (REF && t1 > t0) { // out of the last tile's phase frame
 #pragma unroll
-            for (int d = 0; d < DPT; ++d) rotate_acc<TBL, (FORM & FORM_SWZ) != 0>(ar[d], ai[d], table, rc[d].n_ref, rc[d].phi, pc, SG);
+            for (int d = 0; d < DPT; ++d)
+                rotate_acc<TBL, (FORM & FORM_SWZ) != 0>(ar[d], ai[d], table, rc[RT ? 0 : d].n_ref, rc[RT ? 0 : d].phi, pc, SG);
         }
     };
     if (row)
@@ -797,8 +878,9 @@ const KernelEntry *kernel_table(int *count)
         // small problems: fewer points per thread, and a 2048-entry table (8 sincospi per thread and block)
         make_entry<2, 256, 3, 2048, 2, FORM_TAN | FORM_POLAR>("dpt2 tile256x3 table2048 tan polar"),
         make_entry<1, 128, 4, 2048, 2, FORM_TAN | FORM_POLAR>("dpt1 tile128x4 table2048 tan polar"),
-        // REFERENCED keeps more state per detector point in registers: 2 points per thread
-        make_entry<2, 256, 3, 4096, 2, FORM_DEFAULT | FORM_E2>("dpt2 tile256x3 table4096 tan polar shortcos wfold e2 2 blocks/SM"),
+        // REFERENCED: |e|^2 row + row expansion on planar-row blocks (20.75 FP64 instructions per pair there, 26 in the
+        // general loop, which spills a little at 4 points per thread and is still faster than the 2-point form)
+        make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT | FORM_E2 | FORM_ROWT>("dpt4 tile256x3 table4096 wfold e2 row expansion 2 blocks/SM"),
 #ifdef AKB_AB_VARIANTS
         // 4: the round-1 default (scaled table entry, 27.5 / 31 instructions per pair)
         make_entry<4, 256, 3, 4096, 2, FORM_TAN | FORM_POLAR | FORM_SHORTCOS>(
@@ -811,8 +893,9 @@ const KernelEntry *kernel_table(int *count)
         // 8: REFERENCED candidates: 4 points per thread with the |e|^2 row; 9: 2 points without it (round-2 first form)
         make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT | FORM_E2>("dpt4 tile256x3 table4096 wfold e2 2 blocks/SM"),
         make_entry<2, 256, 3, 4096, 2, FORM_DEFAULT>("dpt2 tile256x3 table4096 wfold 2 blocks/SM"),
-        // 10: the default with an XOR-swizzled table
+        // 10: the default with an XOR-swizzled table; 11: REFERENCED, 2 points per thread with the |e|^2 row, no row expansion
         make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT | FORM_SWZ>("dpt4 tile256x3 table4096 wfold swizzled table"),
+        make_entry<2, 256, 3, 4096, 2, FORM_DEFAULT | FORM_E2>("dpt2 tile256x3 table4096 wfold e2 2 blocks/SM"),
 #endif
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));
@@ -1015,14 +1098,21 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
         }
     } packed_s{st}, partial_s{st};
     const int rows = rows_of(ke.form);
-    AKB_CUDA(cudaMallocAsync(&packed_s.p, (size_t)tiles_total * (rows * TILE + HEAD) * sizeof(double), st));
+    const size_t packed_doubles = (size_t)tiles_total * (rows * TILE + HEAD);
+    AKB_CUDA(cudaMallocAsync(&packed_s.p, (packed_doubles + 8) * sizeof(double), st)); // + the source bounding box (FORM_ROWT)
     if (splits > 1) AKB_CUDA(cudaMallocAsync(&partial_s.p, (size_t)splits * M * 2 * sizeof(double), st));
     double *const packed = packed_s.p, *const partial = partial_s.p;
 
     PhaseConst pc = make_phase_const(k, ke.table);
+    unsigned long long *bbox = nullptr;
+    if ((ke.form & FORM_ROWT) && mode == AKB_PHASE_REFERENCED) {
+        bbox = reinterpret_cast<unsigned long long *>(packed + packed_doubles);
+        AKB_CUDA(cudaMemsetAsync(bbox, 0xFF, 3 * sizeof(unsigned long long), st)); // minima start at the largest key
+        AKB_CUDA(cudaMemsetAsync(bbox + 3, 0x00, 3 * sizeof(unsigned long long), st));
+    }
     pack_sources_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, st>>>(
         src_x, src_y, src_z, src_u, src_ds, N, padded, TILE, mode == AKB_PHASE_REFERENCED ? 1 : 0,
-        (ke.form & FORM_POLAR) ? 1 : 0, rows, pc.im_sign, pc.inv_u, pc.neg_u_hi, pc.neg_u_lo, packed);
+        (ke.form & FORM_POLAR) ? 1 : 0, rows, pc.im_sign, pc.inv_u, pc.neg_u_hi, pc.neg_u_lo, packed, bbox);
     AKB_LAUNCH_CHECK();
 
     double *dst = splits > 1 ? partial : out;

@@ -445,7 +445,8 @@ def run_ours(args):
             L.akb_fresnel_last_timing(ctypes.byref(p_ms), None, None, None, None)
             phase_modes[mode_name] = {
                 "terms_per_s": terms_step / (p_ms.value * 1e-3),
-                "rel_l2_vs_faithful": float(torch.linalg.vector_norm(fm - ref_field) / torch.linalg.vector_norm(ref_field))}
+                "rel_l2_vs_faithful": float(torch.linalg.vector_norm(fm - ref_field) / torch.linalg.vector_norm(ref_field)),
+                "peak_pixel_same_as_faithful": int(fm.abs().argmax()) == int(ref_field.abs().argmax())}
             del fm
         result["phase_modes"] = phase_modes
         result["roofline_ray"] = bench_ray_c2(akb, workloads, torch, dev, peaks, peak_src)
@@ -580,13 +581,15 @@ def bench_m2m(akb, handoff, raytrace, workloads, torch, dev, L, fp64_peak, costs
     gen = (costs or {}).get("general") or {}
     rate = out["faithful"]["terms_per_s"]
     achieved = rate * ALG_FLOP_PER_TERM / 1e12
+    from akbraytracing_b200 import _lib as _l
+    names = {_l.PHASE_FAITHFUL: "faithful", _l.PHASE_EXACT: "exact", _l.PHASE_REFERENCED: "referenced"}
     return {"kernel": "fresnel_pairs_kernel<faithful>, general loop (irregular detector set)",
             "workload": f"AKB mirror 1 (1e6 points) -> first {front.shape[1]} points of mirror 2, {terms:.3g} terms per launch",
             "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
             "traffic": None, "fp64_instr_per_term": gen.get("fp64_instr_per_pair"),
             "executed_flop_per_term": gen.get("exec_flop_per_pair"),
             "frac_exec": rate * gen["exec_flop_per_pair"] / 1e12 / fp64_peak if gen.get("exec_flop_per_pair") else None,
-            "modes": out, "auto_phase_mode": {akb.PHASE_FAITHFUL: "faithful", akb.PHASE_EXACT: "exact"}[auto],
+            "modes": out, "auto_phase_mode": names[auto],
             "parity_sample": "64 random detector points x 1e6 sources vs oracle/akb_oracle.c",
             "timing": "CUDA events inside the library around the pair kernel, best of 2 after a warm-up"}
 

@@ -31,6 +31,16 @@ def test_default_pair_kernel_instruction_mix(lib_path):
     assert row["three_read_per_pair"] <= 5.5 and gen["three_read_per_pair"] <= 5.5
 
 
+def test_referenced_pair_kernel_instruction_mix(lib_path):
+    """AKB_PHASE_REFERENCED: 20.75 FP64 instructions per pair on planar-row blocks (row expansion: one square root per
+    four pairs), 26 in the general loop, and no square-root / reciprocal built-in call in either loop."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from tools import sass_cost
+    c = sass_cost.kernel_loops(lib_path, sass_cost.REFERENCED_KERNEL)
+    assert c["planar_row"]["fp64_instr_per_pair"] == 20.75 and c["general"]["fp64_instr_per_pair"] == 26.0
+
+
 def test_library_is_sm100a_with_tma_and_mbarrier(lib_path):
     elf = subprocess.run(["cuobjdump", "-lelf", lib_path], capture_output=True, text=True).stdout
     assert "sm_100a" in elf

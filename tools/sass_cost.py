@@ -16,6 +16,8 @@ import sys
 # fresnel_pairs_kernel<DPT=4, MODE=FAITHFUL, TILE=256, STAGES=3, TBL=4096, MINB=2, FORM=15, SPI=2, THREADS=256>
 DEFAULT_KERNEL = "fresnel_pairs_kernelILi4ELi0ELi256ELi3ELi4096ELi2ELi15ELi2ELi256E"
 DEFAULT_PAIRS = 8  # 4 detector points x 2 sources per loop iteration
+# the REFERENCED kernel: MODE=2, FORM=tan|polar|shortcos|wfold|e2|rowt = 95
+REFERENCED_KERNEL = "fresnel_pairs_kernelILi4ELi2ELi256ELi3ELi4096ELi2ELi95ELi2ELi256E"
 
 
 def _functions(lib):
@@ -79,15 +81,20 @@ def loop_cost(body, pairs):
             "three_read_per_pair": three / pairs, "model_cycles_per_pair": cyc / pairs, "other_instr_per_pair": other / pairs}
 
 
-def default_kernel_loops(lib):
-    """{'planar_row': {...}, 'general': {...}} for the default FAITHFUL pair kernel of `lib`."""
+def kernel_loops(lib, kernel, pairs=DEFAULT_PAIRS):
+    """{'planar_row': {...}, 'general': {...}} for the pair kernel whose mangled name contains `kernel`."""
     for name, ins in _functions(lib):
-        if DEFAULT_KERNEL in name:
-            costs = sorted((loop_cost(body, DEFAULT_PAIRS) for _, body in hot_loops(ins)), key=lambda c: c["fp64_instr_per_pair"])
+        if kernel in name:
+            costs = sorted((loop_cost(body, pairs) for _, body in hot_loops(ins)), key=lambda c: c["fp64_instr_per_pair"])
             if len(costs) != 2:
                 raise RuntimeError(f"expected the planar-row and the general loop, found {len(costs)} hot loops")
-            return {"kernel": DEFAULT_KERNEL, "planar_row": costs[0], "general": costs[1]}
-    raise RuntimeError("default pair kernel not found in " + lib)
+            return {"kernel": kernel, "planar_row": costs[0], "general": costs[1]}
+    raise RuntimeError(f"pair kernel {kernel} not found in {lib}")
+
+
+def default_kernel_loops(lib):
+    """The default FAITHFUL pair kernel of `lib` (what bench.py times)."""
+    return kernel_loops(lib, DEFAULT_KERNEL)
 
 
 def main():
