@@ -867,18 +867,19 @@ def test_referenced_row_expansion_and_its_guard(akb, golden):
     1e-11 rad, the guard sends every block to the general loop, same accuracy."""
     rng = np.random.default_rng(31)
     k = 2 * np.pi / 1.35e-9
-    N = 3000  # 12 source tiles x 256x256 detector points: large enough for the 4-points-per-thread REFERENCED kernel
+    N = 3000  # 12 source tiles x 512x512 detector points: large enough for the size-aware choice to take the
+              # 4-points-per-thread REFERENCED kernel (smaller problems run the 1- / 2-point kernels, which have no row expansion)
     sx = rng.uniform(-0.01, 0.01, N); sy = rng.uniform(-2e-3, 2e-3, N); sz = rng.uniform(-2e-3, 2e-3, N)
     u = rng.normal(size=N) + 1j * rng.normal(size=N); ds = rng.uniform(1e-9, 2e-9, N)
     for pitch, expect_row in ((4e-9, True), (2e-6, False)):
-        G = 256
+        G = 512
         yy, zz = np.meshgrid(3e-4 + pitch * np.arange(G), -2e-4 + pitch * np.arange(G))
         x = np.full(G * G, 0.15); y = yy.ravel(); z = zz.ravel()
         _row_blocks(akb)
         got = akb.fresnel_sum(x, y, z, sx, sy, sz, u, k, ds, mode=akb.PHASE_REFERENCED)
         took_row = _row_blocks(akb) > 0
         assert took_row == expect_row, (pitch, took_row)
-        sel = np.arange(0, G * G, 1637)[:24]
+        sel = np.arange(0, G * G, 10007)[:24]
         truth = _mp_truth(x[sel], y[sel], z[sel], sx, sy, sz, u, ds, k)
         faithful = akb.fresnel_sum(x[sel], y[sel], z[sel], sx, sy, sz, u, k, ds)
         e_ref, e_faith = rel_l2(got[sel], truth), rel_l2(faithful, truth)
