@@ -843,7 +843,20 @@ struct KernelEntry {
     int smem;
 };
 
-template <int DPT, int TILE, int STAGES, int TBL, int MINB, int FORM, int SPI = 2, int THREADS = 256>
+// MODES: bit m set = the entry is built for phase mode m (an entry the default choice never takes in some mode is not
+// compiled for it: every instantiation is ~100 KB of SASS and seconds of ptxas)
+constexpr int BUILD_F = 1 << AKB_PHASE_FAITHFUL, BUILD_E = 1 << AKB_PHASE_EXACT, BUILD_R = 1 << AKB_PHASE_REFERENCED, BUILD_ALL = BUILD_F | BUILD_E | BUILD_R;
+
+template <int DPT, int MODE, int TILE, int STAGES, int TBL, int MINB, int FORM, int SPI, int THREADS, bool BUILD>
+const void *pair_kernel_ptr()
+{
+    if constexpr (BUILD)
+        return reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, MODE, TILE, STAGES, TBL, MINB, FORM, SPI, THREADS>);
+    else
+        return nullptr;
+}
+
+template <int DPT, int TILE, int STAGES, int TBL, int MINB, int FORM, int SPI = 2, int THREADS = 256, int MODES = BUILD_ALL>
 KernelEntry make_entry(const char *name)
 {
     KernelEntry e;
@@ -852,9 +865,9 @@ KernelEntry make_entry(const char *name)
     e.tile = TILE;
     e.stages = STAGES;
     e.table = TBL;
-    e.fn[0] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_FAITHFUL, TILE, STAGES, TBL, MINB, FORM, SPI, THREADS>);
-    e.fn[1] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_EXACT, TILE, STAGES, TBL, MINB, FORM, SPI, THREADS>);
-    e.fn[2] = reinterpret_cast<const void *>(&fresnel_pairs_kernel<DPT, AKB_PHASE_REFERENCED, TILE, STAGES, TBL, MINB, FORM, SPI, THREADS>);
+    e.fn[0] = pair_kernel_ptr<DPT, AKB_PHASE_FAITHFUL, TILE, STAGES, TBL, MINB, FORM, SPI, THREADS, (MODES & BUILD_F) != 0>();
+    e.fn[1] = pair_kernel_ptr<DPT, AKB_PHASE_EXACT, TILE, STAGES, TBL, MINB, FORM, SPI, THREADS, (MODES & BUILD_E) != 0>();
+    e.fn[2] = pair_kernel_ptr<DPT, AKB_PHASE_REFERENCED, TILE, STAGES, TBL, MINB, FORM, SPI, THREADS, (MODES & BUILD_R) != 0>();
     e.smem = PairCfg<TILE, STAGES, TBL, FORM>::kSmemBytes;
     e.form = FORM;
     e.threads = THREADS;
@@ -874,13 +887,14 @@ const KernelEntry *kernel_table(int *count)
         // threads per SM (measured in round 1: 3 blocks/SM at 80 registers spill, 1 block/SM starves the FP64
         // pipe, block sizes that are not a multiple of 4 warps lose 10-20 %, one 640/768-thread block per SM
         // sharing one table loses 2-4 %)
-        make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT>("dpt4 tile256x3 table4096 tan polar shortcos wfold 2 blocks/SM"),
+        make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT, 2, 256, BUILD_F | BUILD_E>("dpt4 tile256x3 table4096 tan polar shortcos wfold 2 blocks/SM"),
         // small problems: fewer points per thread, and a 2048-entry table (8 sincospi per thread and block)
         make_entry<2, 256, 3, 2048, 2, FORM_TAN | FORM_POLAR>("dpt2 tile256x3 table2048 tan polar"),
         make_entry<1, 128, 4, 2048, 2, FORM_TAN | FORM_POLAR>("dpt1 tile128x4 table2048 tan polar"),
         // REFERENCED: |e|^2 row + row expansion on planar-row blocks (20.75 FP64 instructions per pair there, 26 in the
         // general loop, which spills a little at 4 points per thread and is still faster than the 2-point form)
-        make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT | FORM_E2 | FORM_ROWT>("dpt4 tile256x3 table4096 wfold e2 row expansion 2 blocks/SM"),
+        make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT | FORM_E2 | FORM_ROWT, 2, 256, BUILD_R>(
+            "dpt4 tile256x3 table4096 wfold e2 row expansion 2 blocks/SM"),
 #ifdef AKB_AB_VARIANTS
         // 4: the round-1 default (scaled table entry, 27.5 / 31 instructions per pair)
         make_entry<4, 256, 3, 4096, 2, FORM_TAN | FORM_POLAR | FORM_SHORTCOS>(
@@ -942,6 +956,7 @@ int resident_blocks(const KernelEntry &ke, int mode)
     const int v = (int)(&ke - e);
     if (v >= 0 && v < 16 && cache[v][mode] > 0) return cache[v][mode];
     int per_sm = 1;
+    if (!ke.fn[mode]) return 1; // not built for this mode (only reachable through AKB_FRESNEL_VARIANT)
     if (cudaFuncSetAttribute(ke.fn[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, ke.smem) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ke.fn[mode], ke.threads, ke.smem) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
@@ -1066,6 +1081,7 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     const int sms = sm_count(device);
     const KernelEntry &ke = selected_kernel(mode, M, N, sms);
     const void *kern = ke.fn[mode];
+    AKB_REQUIRE(kern != nullptr, "the kernel variant forced with AKB_FRESNEL_VARIANT is not built for this phase mode");
     const int TILE = ke.tile;
 
     const int tiles_total = (int)((N + TILE - 1) / TILE);

@@ -110,7 +110,9 @@ int akb_shard_range(int64_t total, int nranks, int rank, int64_t *begin, int64_t
  *   det_x/y/z          float64[M], the FULL detector arrays on every rank (the reference splits views of them)
  *   src_*              as akb_fresnel_sum; with broadcast_sources != 0 rank 0's source arrays are first replicated
  *                      into the other ranks' (caller-allocated) buffers with ncclBroadcast -- the reference keeps
- *                      the back surface on device 0 and reads it by peer access (GPU0402:36-38)
+ *                      the back surface on device 0 and reads it by peer access (GPU0402:36-38); src_ds must then be
+ *                      NULL on every rank or on none (the broadcasts are collective)
+ * Like every collective, the call must be made by all nranks ranks with the same M, N, mode and flags.
  * NCCL is bound at run time (the libnccl.so.2 already loaded in the process, else the default search path, else
  * $AKB_NCCL_LIB); without it the call fails with AKB_ERR_NCCL when nranks > 1. */
 int akb_fresnel_sum_sharded(void *nccl_comm, int rank, int nranks, const double *det_x, const double *det_y,
