@@ -59,3 +59,35 @@ def test_batched_psf_matches_reference_golden_on_cpu_device(golden):
     assert np.allclose(E[0], g["plain/E"], rtol=1e-9, atol=1e-15)
     with pytest.raises(ValueError):
         compute_psf_fft_batch(g["opd"], g["amp"], 13.5e-9, 1e-4, 0.3, device="cpu")   # needs (P, ny, nx)
+
+
+def test_auto_phase_mode_per_stage():
+    """run_stage_chain(phase_mode='auto'): FAITHFUL where the other modes would leave the 1e-7 margin (the 146 m source ->
+    M1 stage), REFERENCED for a detector plane, EXACT for an irregular detector set (a mirror)."""
+    from akbraytracing_b200 import _lib
+    from akbraytracing_b200.stagechain import auto_phase_mode
+    k = 2 * np.pi / 13.5e-9
+    rng = np.random.default_rng(0)
+    src = np.zeros((3, 1))
+    m1 = np.vstack([146.0 + rng.uniform(-0.03, 0.03, 50), rng.uniform(-2e-3, 2e-3, 50), rng.uniform(-2e-3, 2e-3, 50)])
+    m2 = m1 + np.array([[0.12], [0.0], [0.0]])
+    yy, zz = np.meshgrid(np.linspace(-1e-6, 1e-6, 8), np.linspace(-1e-6, 1e-6, 8))
+    plane = np.vstack([np.full(64, 146.3), yy.ravel(), zz.ravel()])
+    assert auto_phase_mode(k, m1, src) == _lib.PHASE_FAITHFUL        # k r 2^-52 = 1.5e-5
+    assert auto_phase_mode(k, m2, m1) == _lib.PHASE_EXACT            # 0.18 m between two mirrors: 1.9e-8
+    assert auto_phase_mode(k, plane, m2) == _lib.PHASE_REFERENCED    # a plane x = const
+    assert auto_phase_mode(10 * k, plane, m2, tol=1e-9) == _lib.PHASE_FAITHFUL
+
+
+def test_handoff_downsampling_is_every_second_sample():
+    """downsample_array_3_n (AKB_raytrace_20250312.py:13336-13356): count = flag // 2 passes of [::2] per axis."""
+    from akbraytracing_b200.stagechain import _downsample
+    nV, nH = 9, 13
+    cloud = np.arange(3 * nV * nH, dtype=np.float64).reshape(3, nV * nH)
+    g = cloud.reshape(3, nV, nH)
+    out, sv, sh = _downsample(cloud, nV, nH, 0, 0)
+    assert (sv, sh) == (nV, nH) and np.array_equal(out, cloud)
+    out, sv, sh = _downsample(cloud, nV, nH, 2, 0)
+    assert (sv, sh) == (nV, 7) and np.array_equal(out, g[:, :, ::2].reshape(3, -1))
+    out, sv, sh = _downsample(cloud, nV, nH, 4, 2)
+    assert (sv, sh) == (5, 4) and np.array_equal(out, g[:, ::2, ::4].reshape(3, -1))
