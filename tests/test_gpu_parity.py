@@ -906,3 +906,44 @@ def test_device_api_is_cuda_graph_capturable(akb, torch):
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, 2.0 * ref)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fresnel_randomised_geometries_all_modes(akb, seed):
+    """Differential test on random geometries: planar grids of random shape / pitch / orientation in the array (rows along
+    y or along z), irregular clouds, detector sets that straddle the source set's bounding box, either sign of k, with
+    and without ds -- every phase mode against the oracle.  FAITHFUL must sit at the summation-order floor; the other
+    modes within the reference's own rounding noise k r 2^-52 (with a floor for tiny problems)."""
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.choice([1, 2, 255, 256, 257, 1000, 2999]))
+    lam = float(rng.choice([13.5e-9, 1.35e-9]))
+    k = (2 * np.pi / lam) * (1 if rng.random() < 0.8 else -1)
+    dist0 = float(rng.choice([0.03, 0.15, 0.4]))
+    sx = rng.uniform(-0.02, 0.02, N); sy = rng.uniform(-3e-3, 3e-3, N); sz = rng.uniform(-3e-3, 3e-3, N)
+    u = rng.normal(size=N) + 1j * rng.normal(size=N)
+    ds = rng.uniform(1e-9, 2e-9, N) if rng.random() < 0.7 else None
+    kind = seed % 4
+    if kind == 0:      # focal grid, y fastest (np.meshgrid(y, z) order), nanometre to micrometre pitch
+        gy, gz = int(rng.choice([4, 64, 100, 256])), int(rng.choice([3, 33, 64]))
+        pitch = float(rng.choice([2e-9, 5e-8, 3e-6]))
+        yy, zz = np.meshgrid(rng.uniform(-1e-3, 1e-3) + pitch * np.arange(gy), rng.uniform(-1e-3, 1e-3) + pitch * np.arange(gz))
+        x = np.full(gy * gz, dist0); y = yy.ravel(); z = zz.ravel()
+    elif kind == 1:    # the same kind of grid stored z fastest: planar, but rows do not align with the threads
+        g = int(rng.choice([16, 64, 128]))
+        zz, yy = np.meshgrid(1e-7 * np.arange(g), 1e-7 * np.arange(g))
+        x = np.full(g * g, dist0); y = yy.ravel(); z = zz.ravel()
+    elif kind == 2:    # irregular cloud (a mirror surface)
+        M = int(rng.choice([1, 5, 1023, 4097]))
+        x = dist0 + rng.uniform(-0.02, 0.02, M); y = rng.uniform(-2e-3, 2e-3, M); z = rng.uniform(-2e-3, 2e-3, M)
+    else:              # a plane INSIDE the x range of the sources (distance to the bounding box = 0 in x), offset in y
+        g = 64
+        yy, zz = np.meshgrid(0.02 + 1e-8 * np.arange(g), 1e-8 * np.arange(g))
+        x = np.full(g * g, 0.0); y = yy.ravel(); z = zz.ravel()
+    ref = oracle.fresnel_sum(x, y, z, sx, sy, sz, u, k, ds)
+    r_max = float(np.sqrt((np.abs(x).max() + 0.02) ** 2 + (np.abs(y).max() + 3e-3) ** 2 + (np.abs(z).max() + 3e-3) ** 2))
+    noise = max(abs(k) * r_max * 2.0 ** -52 * 4, 1e-11)
+    for mode in (akb.PHASE_FAITHFUL, akb.PHASE_EXACT, akb.PHASE_REFERENCED):
+        got = akb.fresnel_sum(x, y, z, sx, sy, sz, u, k, ds, mode=mode)
+        err = rel_l2(got, ref)
+        tol = 1e-12 if mode == akb.PHASE_FAITHFUL else noise
+        assert err <= tol, (seed, kind, mode, err, tol)
