@@ -702,11 +702,15 @@ def bench_chain(workloads, torch, L, _lib, peaks, peak_src, n=3163, reps=5):
                     best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
             bpr = 48 + 24 * K + 24 + 24 + extra
             gbs = N * bpr / (best * 1e-3) / 1e9
+            hits = K * N / (best * 1e-3)
             out[f"K{K}_{form}"] = {
                 "workload": f"{'KB' if K == 2 else 'AKB'} chain, {N} rays, {K} mirrors + plane + "
                             f"{'segment lengths' if form == 'segments' else 'optical path'}",
                 "bytes_per_ray": bpr, "kernel_ms": best, "achieved": gbs, "frac": gbs / peaks["hbm_gbs"],
-                "rays_per_s": N / (best * 1e-3), "mirror_hits_per_s": K * N / (best * 1e-3), "misses": int(flags[0])}
+                "rays_per_s": N / (best * 1e-3), "mirror_hits_per_s": hits, "misses": int(flags[0]),
+                # second bound: ~206 executed FP64 instructions per mirror hit (ncu op counters of the K = 2 launch,
+                # profiles/r02d_ncu_full_chain_kernel.md) against 148 SM x 64 FP64 lanes x 1.965 GHz
+                "fp64_pipe_frac_est": hits * 206.0 / (148 * 64 * 1.965e9)}
         del pts, last, det, dist, opl, ray, src
         torch.cuda.empty_cache()
     k2 = out["K2_segments"]
