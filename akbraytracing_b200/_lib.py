@@ -33,6 +33,7 @@ SIGNATURES = {
     "akb_trim": (_c_int, [_c_int]),
     "akb_fresnel_sum": (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_dbl, _vp, _c_int, _vp]),
     "akb_fresnel_sum_host": (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_dbl, _vp, _c_int, _c_int]),
+    "akb_fresnel_sum_planes": (_c_int, [_vp, _vp, _c_i64, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_dbl, _vp, _c_int, _vp]),
     "akb_fresnel_sum_sharded": (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_dbl, _vp,
                                           _c_int, _c_int, _vp]),
     "akb_allgather_blocks": (_c_int, [_vp, _c_int, _c_int, _vp, _c_i64, _c_int, _vp]),

@@ -59,7 +59,15 @@ constexpr int HEAD = 4; // per-tile header after the rows: reference point c_T (
 //                 a = (y0 - Y_j)/r,  b = (1 - a^2)/(2 r)  (third order: |a| D^3/(2 r^2), guarded below 1e-11 rad
 //                 per block from the bounding box of the source set), and 1/(2r) to first order: 3 DFMAs instead
 //                 of 10 instructions per pair for three pairs out of four.
-enum { FORM_TAN = 1, FORM_SHORTCOS = 2, FORM_POLAR = 4, FORM_WFOLD = 8, FORM_E2 = 16, FORM_SWZ = 32, FORM_ROWT = 64 };
+//   FORM_PLANES   (FAITHFUL / EXACT, 4 points per thread) through-focus stacks: a thread owns ONE pixel (y, z) on FOUR
+//                 planes x = x_p.  (y - Y_j)^2 and (z - Z_j)^2 are then one value per (thread, source), and (x_p - X_j)^2
+//                 one value per (plane, source) that the block computes once per tile (row 0 in place of the sx row,
+//                 three more rows in a scratch area): r^2 costs 2 additions + 1 shared instruction per pair instead
+//                 of 4.5, with the reference's operations in the reference's order.  Launched by akb_fresnel_sum_planes
+//                 only: det_x = the plane positions, M = pixels per plane, pc.planes = number of planes, grid.z = groups
+//                 of four planes, out = [plane][pixel].
+enum { FORM_TAN = 1, FORM_SHORTCOS = 2, FORM_POLAR = 4, FORM_WFOLD = 8, FORM_E2 = 16, FORM_SWZ = 32, FORM_ROWT = 64,
+       FORM_PLANES = 128 };
 // rows of a packed source tile: sx, sy, sz, then (w_re, w_im) or (|w|, -frac(arg w), MAGIC - m [, -|w|/2 [, |e|^2]])
 __host__ __device__ constexpr int rows_of(int form)
 {
@@ -80,6 +88,7 @@ struct PhaseConst {
     // values in vector registers for that code and then feeds the pair loop's DFMAs from those registers: three
     // register reads per DFMA instead of two plus a uniform operand (+1.75 FP64-pipe cycles each, three per pair).
     double tq_hi, tq_lo, tu;
+    int planes; // FORM_PLANES: number of detector planes (0 otherwise)
 };
 
 // order-preserving map double -> unsigned 64-bit (for atomicMin / atomicMax on coordinates) and back
@@ -482,7 +491,8 @@ struct PairCfg {
     // tiles | mbarriers (padded to 16 B) | 2 loop constants | table
     static constexpr int kBarBytes = (STAGES * 8 + 15) & ~15;
     static constexpr int kTableOffset = STAGES * kTileBytes + kBarBytes + 16;
-    static constexpr int kSmemBytes = kTableOffset + kTableBytes;
+    static constexpr int kScratchOffset = kTableOffset + kTableBytes; // FORM_PLANES: (x_p - X_j)^2 of planes 1..3
+    static constexpr int kSmemBytes = kScratchOffset + ((FORM & FORM_PLANES) ? 3 * TILE * 8 : 0);
 };
 
 template <int DPT, int MODE, int TILE, int STAGES, int TBL, int MINB, int FORM, int SPI, int THREADS>
@@ -499,6 +509,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
     constexpr bool REF = MODE == AKB_PHASE_REFERENCED;
     constexpr bool E2 = (FORM & FORM_E2) != 0;
     constexpr bool ROWT = REF && (FORM & FORM_ROWT) != 0;
+    constexpr bool PL = (FORM & FORM_PLANES) != 0;
+    static_assert(!PL || (DPT == 4 && SPI == 2 && MODE != AKB_PHASE_REFERENCED), "FORM_PLANES: 4 planes per thread, FAITHFUL / EXACT");
     static_assert(!(FORM & FORM_ROWT) || (E2 && DPT >= 2), "FORM_ROWT builds on FORM_E2 and several points per thread");
     static_assert(SPI == 1 || SPI == 2, "1 or 2 sources per loop iteration");
     constexpr int NP = SPI * DPT; // pairs per loop iteration: DPT detector points x SPI sources
@@ -512,16 +524,26 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
     const int t0 = blockIdx.y * tiles_per_split;
     const int t1 = min(t0 + tiles_per_split, tiles_total);
     // a thread owns DPT CONSECUTIVE detector points: in a meshgrid-ordered focal grid they lie in one row
-    const long long base = ((long long)blockIdx.x * THREADS + threadIdx.x) * DPT;
+    // (FORM_PLANES: one pixel on DPT consecutive planes)
+    const long long base = PL ? (long long)blockIdx.x * THREADS + threadIdx.x : ((long long)blockIdx.x * THREADS + threadIdx.x) * DPT;
+    double *scratch = reinterpret_cast<double *>(smem_raw + Cfg::kScratchOffset);
 
     double X[DPT], Y[DPT], Z[DPT], ar[DPT], ai[DPT];
 #pragma unroll
     for (int d = 0; d < DPT; ++d) {
-        long long i = base + d;
-        long long ic = i < M ? i : M - 1;
-        X[d] = det_x[ic];
-        Y[d] = det_y[ic];
-        Z[d] = det_z[ic];
+        if (PL) {
+            const int pl = (int)blockIdx.z * DPT + d;
+            const long long ic = base < M ? base : M - 1;
+            X[d] = det_x[pl < pc.planes ? pl : pc.planes - 1];
+            Y[d] = det_y[ic];
+            Z[d] = det_z[ic];
+        } else {
+            long long i = base + d;
+            long long ic = i < M ? i : M - 1;
+            X[d] = det_x[ic];
+            Y[d] = det_y[ic];
+            Z[d] = det_z[ic];
+        }
         ar[d] = 0.0;
         ai[d] = 0.0;
     }
@@ -531,8 +553,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
     // source): 4.5 instead of 8 FP64 instructions for r^2 per pair, bit-identical results.  Detected here
     // from the coordinates themselves (block-uniform vote), so irregular detector sets (mirror surfaces)
     // simply take the general loop.
-    bool row = false;
-    {
+    bool row = PL; // FORM_PLANES: by construction
+    if (!PL) {
         const long long i0 = (long long)blockIdx.x * THREADS * DPT;
         const double x0 = det_x[i0 < M ? i0 : M - 1];
         bool mine = true;
@@ -625,7 +647,14 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
             if (ROW) { // the sx row becomes fl((x0 - sx)^2), CPU0402:76-77 (REFERENCED: e_x (e_x - 2 D_x);
                        // FORM_E2: the |e|^2 row becomes |e|^2 + e_x (-2 D_x))
                 for (int q = threadIdx.x; q < TILE; q += THREADS) {
-                    if (REF && E2) {
+                    if (PL) { // (x_p - X_j)^2 for the block's four planes: CPU0402:76-77 per plane
+                        const double sxq = T[q];
+#pragma unroll
+                        for (int d = 0; d < DPT; ++d) {
+                            const double ddx = sub(X[d], sxq);
+                            (d == 0 ? T[q] : scratch[(d - 1) * TILE + q]) = mul(ddx, ddx);
+                        }
+                    } else if (REF && E2) {
                         T[7 * TILE + q] = fma_(T[q], rc[0].gx, T[7 * TILE + q]);
                     } else {
                         const double ddx = REF ? add(T[q], rc[0].gx) : sub(X[0], T[q]);
@@ -655,7 +684,21 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
 #pragma unroll
                     for (int q = 0; q < SPI; ++q) S[5][q] = magic;
                 }
-                double ddz[SPI], dzz[SPI];
+                double ddz[SPI], dzz[SPI], ddy[SPI], dyy[SPI], dxp[DPT][SPI];
+                if (PL) { // one pixel per thread: the y term is shared by its four planes like the z term
+#pragma unroll
+                    for (int q = 0; q < SPI; ++q) {
+                        ddy[q] = sub(Y[0], S[1][q]);
+                        dyy[q] = mul(ddy[q], ddy[q]);
+                        dxp[0][q] = S[0][q];
+                    }
+#pragma unroll
+                    for (int d = 1; d < DPT; ++d) {
+                        const double2 v = *reinterpret_cast<const double2 *>(scratch + (d - 1) * TILE + j);
+                        dxp[d][0] = v.x;
+                        dxp[d][SPI - 1] = v.y;
+                    }
+                }
                 if (ROW) {
 #pragma unroll
                     for (int q = 0; q < SPI; ++q) {
@@ -692,6 +735,11 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
                             a[i] = pair_phase_a_ref_row<E2>(rc[d], dzz[q], S[1][q], pc, S[5][q]);
                         } else if (REF) {
                             a[i] = pair_phase_a_ref<E2>(rc[d], S[0][q], S[1][q], S[2][q], S[7][q], pc, S[5][q]);
+                        } else if (PL) {
+                            // (dx*dx + dy*dy) + dz*dz, CPU0402:76-80 (EXACT: the fused form of pair_phase_a)
+                            const double s2 = MODE == AKB_PHASE_FAITHFUL ? add(add(dxp[d][q], dyy[q]), dzz[q])
+                                                                          : fma_(ddz[q], ddz[q], fma_(ddy[q], ddy[q], dxp[d][q]));
+                            a[i] = pair_phase_a_from_s<MODE>(s2, pc, S[5][q]);
                         } else if (ROW) {
                             a[i] = pair_phase_a_row<MODE>(S[0][q], Y[d], S[1][q], ddz[q], dzz[q], pc, S[5][q]);
                         } else {
@@ -776,11 +824,17 @@ __global__ void __launch_bounds__(THREADS, MINB) fresnel_pairs_kernel(
     else
         run_tiles(std::false_type{});
 
-    double2 *o = reinterpret_cast<double2 *>(out) + (long long)blockIdx.y * M;
+    double2 *o = reinterpret_cast<double2 *>(out) + (long long)blockIdx.y * (PL ? M * pc.planes : M);
 #pragma unroll
     for (int d = 0; d < DPT; ++d) {
-        long long i = base + d;
-        if (i < M) o[i] = make_double2(ar[d], mul((FORM & FORM_WFOLD) ? -pc.im_sign : pc.im_sign, ai[d]));
+        const double2 v = make_double2(ar[d], mul((FORM & FORM_WFOLD) ? -pc.im_sign : pc.im_sign, ai[d]));
+        if (PL) {
+            const int pl = (int)blockIdx.z * DPT + d;
+            if (pl < pc.planes && base < M) o[(long long)pl * M + base] = v;
+        } else {
+            long long i = base + d;
+            if (i < M) o[i] = v;
+        }
     }
 }
 
@@ -833,6 +887,7 @@ PhaseConst make_phase_const(double k, int table)
     pc.tq_hi = pc.q_hi;
     pc.tq_lo = pc.q_lo;
     pc.tu = pc.u;
+    pc.planes = 0;
     return pc;
 }
 
@@ -1054,10 +1109,21 @@ char *host_stage()
 
 } // namespace
 
-extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const double *det_z, int64_t M,
-                               const double *src_x, const double *src_y, const double *src_z,
-                               const double *src_u, const double *src_ds, int64_t N, double k, double *out,
-                               int mode, void *stream)
+namespace {
+
+// the through-focus kernel (FORM_PLANES): one pixel on four planes per thread; FAITHFUL and EXACT only
+const KernelEntry &planes_kernel()
+{
+    static const KernelEntry e = make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT | FORM_PLANES, 2, 256, BUILD_F | BUILD_E>(
+        "dpt4 tile256x3 table4096 wfold, one pixel x four planes per thread");
+    return e;
+}
+
+// planes == 0: det_x/y/z are M detector points.  planes > 0 (akb_fresnel_sum_planes): det_x holds the `planes` plane
+// positions, det_y/z the M pixels of one plane, out is [planes][M].
+int fresnel_sum_impl(const double *det_x, const double *det_y, const double *det_z, int64_t M, int planes,
+                     const double *src_x, const double *src_y, const double *src_z, const double *src_u,
+                     const double *src_ds, int64_t N, double k, double *out, int mode, void *stream)
 {
     AKB_REQUIRE(M >= 0 && N >= 0, "M and N must be non-negative");
     AKB_REQUIRE(mode == AKB_PHASE_FAITHFUL || mode == AKB_PHASE_EXACT || mode == AKB_PHASE_REFERENCED,
@@ -1065,8 +1131,9 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     if (M == 0) return AKB_OK;
     AKB_REQUIRE(det_x && det_y && det_z && out, "detector/out pointers must not be NULL");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t M_out = planes > 0 ? M * planes : M; // field values written
     if (N == 0) { // empty sum (np.sum of an empty array) = 0
-        fill_zero_kernel<<<(unsigned)((2 * M + 255) / 256), 256, 0, st>>>(out, 2 * M);
+        fill_zero_kernel<<<(unsigned)((2 * M_out + 255) / 256), 256, 0, st>>>(out, 2 * M_out);
         AKB_LAUNCH_CHECK();
         return AKB_OK;
     }
@@ -1079,7 +1146,7 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     AKB_CUDA(cudaGetDevice(&device));
     tune_pool(device);
     const int sms = sm_count(device);
-    const KernelEntry &ke = selected_kernel(mode, M, N, sms);
+    const KernelEntry &ke = planes > 0 ? planes_kernel() : selected_kernel(mode, M, N, sms);
     const void *kern = ke.fn[mode];
     AKB_REQUIRE(kern != nullptr, "the kernel variant forced with AKB_FRESNEL_VARIANT is not built for this phase mode");
     const int TILE = ke.tile;
@@ -1093,8 +1160,10 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     AKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ke.smem));
     const int per_sm = resident_blocks(ke, mode);
     const long long slots = (long long)sms * per_sm;
-    const long long blocks_x = (M + ke.threads * ke.dpt - 1) / (ke.threads * ke.dpt);
-    const int splits = plan_splits(blocks_x, tiles_total, slots, M, nullptr);
+    const long long blocks_x = planes > 0 ? (M + ke.threads - 1) / ke.threads : (M + ke.threads * ke.dpt - 1) / (ke.threads * ke.dpt);
+    const int groups = planes > 0 ? (planes + ke.dpt - 1) / ke.dpt : 1; // grid.z: groups of four planes
+    AKB_REQUIRE(groups <= 65535, "at most 262140 planes per call");
+    const int splits = plan_splits(blocks_x * groups, tiles_total, slots, M_out, nullptr);
     int tiles_per_split = (tiles_total + splits - 1) / splits;
 
     int rc;
@@ -1116,10 +1185,11 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
     const int rows = rows_of(ke.form);
     const size_t packed_doubles = (size_t)tiles_total * (rows * TILE + HEAD);
     AKB_CUDA(cudaMallocAsync(&packed_s.p, (packed_doubles + 8) * sizeof(double), st)); // + the source bounding box (FORM_ROWT)
-    if (splits > 1) AKB_CUDA(cudaMallocAsync(&partial_s.p, (size_t)splits * M * 2 * sizeof(double), st));
+    if (splits > 1) AKB_CUDA(cudaMallocAsync(&partial_s.p, (size_t)splits * M_out * 2 * sizeof(double), st));
     double *const packed = packed_s.p, *const partial = partial_s.p;
 
     PhaseConst pc = make_phase_const(k, ke.table);
+    pc.planes = planes;
     unsigned long long *bbox = nullptr;
     if ((ke.form & FORM_ROWT) && mode == AKB_PHASE_REFERENCED) {
         bbox = reinterpret_cast<unsigned long long *>(packed + packed_doubles);
@@ -1139,19 +1209,69 @@ extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const d
         const double *pk = packed;
         void *args[] = {(void *)&det_x, (void *)&det_y, (void *)&det_z, (void *)&M_, (void *)&pk, (void *)&tt,
                         (void *)&tiles_per_split, (void *)&n_padded, (void *)&pc, (void *)&dst};
-        dim3 grid((unsigned)blocks_x, (unsigned)splits);
+        dim3 grid((unsigned)blocks_x, (unsigned)splits, (unsigned)groups);
         AKB_CUDA(cudaLaunchKernel(kern, grid, dim3(ke.threads), args, (size_t)ke.smem, st));
         count_launch();
     }
     if ((rc = timing_mark(2, st))) return rc;
     if (splits > 1) {
-        reduce_partials_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(
-            reinterpret_cast<const double2 *>(partial), splits, M, reinterpret_cast<double2 *>(out));
+        reduce_partials_kernel<<<(unsigned)((M_out + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const double2 *>(partial), splits, M_out, reinterpret_cast<double2 *>(out));
         AKB_LAUNCH_CHECK();
     }
     if ((rc = timing_mark(3, st))) return rc;
     g_timing.valid = g_timing.enabled;
     return AKB_OK;
+}
+
+// (plane, pixel) -> flat detector arrays, for the phase mode the four-plane kernel is not built for
+__global__ void expand_planes_kernel(const double *__restrict__ x_planes, const double *__restrict__ y, const double *__restrict__ z,
+                                     long long M, int planes, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * planes) return;
+    const long long p = i / M, q = i - p * M;
+    fx[i] = x_planes[p];
+    fy[i] = y[q];
+    fz[i] = z[q];
+}
+
+} // namespace
+
+extern "C" int akb_fresnel_sum(const double *det_x, const double *det_y, const double *det_z, int64_t M,
+                               const double *src_x, const double *src_y, const double *src_z,
+                               const double *src_u, const double *src_ds, int64_t N, double k, double *out,
+                               int mode, void *stream)
+{
+    return fresnel_sum_impl(det_x, det_y, det_z, M, 0, src_x, src_y, src_z, src_u, src_ds, N, k, out, mode, stream);
+}
+
+extern "C" int akb_fresnel_sum_planes(const double *det_y, const double *det_z, int64_t M, const double *x_planes, int planes,
+                                      const double *src_x, const double *src_y, const double *src_z, const double *src_u,
+                                      const double *src_ds, int64_t N, double k, double *out, int mode, void *stream)
+{
+    AKB_REQUIRE(planes >= 0 && M >= 0, "planes and M must be non-negative");
+    if (planes == 0 || M == 0) return AKB_OK;
+    AKB_REQUIRE(x_planes && det_y && det_z && out, "detector/out pointers must not be NULL");
+    if (mode != AKB_PHASE_REFERENCED)
+        return fresnel_sum_impl(x_planes, det_y, det_z, M, planes, src_x, src_y, src_z, src_u, src_ds, N, k, out, mode, stream);
+    // REFERENCED: the plane-major flat detector set; every 1024-point block lies in one row of one plane and takes the
+    // row-expansion loop, the fastest one there is
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total = (long long)M * planes;
+    double *flat = nullptr;
+    AKB_CUDA(cudaMallocAsync(&flat, 3 * (size_t)total * sizeof(double), st));
+    expand_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_planes, det_y, det_z, M, planes, flat, flat + total, flat + 2 * total);
+    int rc = AKB_OK;
+    if (cudaGetLastError() != cudaSuccess) {
+        set_error("expand_planes_kernel launch failed");
+        rc = AKB_ERR_CUDA;
+    } else {
+        count_launch();
+        rc = fresnel_sum_impl(flat, flat + total, flat + 2 * total, total, 0, src_x, src_y, src_z, src_u, src_ds, N, k, out, mode, stream);
+    }
+    cudaFreeAsync(flat, st);
+    return rc;
 }
 
 extern "C" int akb_fresnel_timing(int enable)

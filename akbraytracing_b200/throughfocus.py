@@ -5,10 +5,11 @@ The reference computes one plane per run of the Wavecalc script (focal grid and 
 Wavecalc_raytrace_fromData_CPU0402.py:330-370) and one PSF per call of ``compute_psf_fft`` (psf_fft.py:29-125, fed by
 ``psf_calc``, AKB_raytrace_20250312.py:1121-1200 with ``pad_factor=16``).  Here
 
-* ``fresnel_sum_planes`` flattens planes x pixels into ONE detector set (plane-major, so every 1024-point block of
-  the pair kernel lies in one row of one plane and takes the planar-row loop) and runs one ``akb_fresnel_sum`` -- or,
-  under torch.distributed, one ``akb_fresnel_sum_sharded``: the flat index is split like ``array_split`` over the
-  ranks and all-gathered (SURVEY.md 8e);
+* ``fresnel_sum_planes`` is one ``akb_fresnel_sum_planes`` launch: a thread keeps one (y, z) pixel for four planes, so
+  the y and z terms of r^2 are shared by four pairs and the x term by the whole block (24 FP64 instructions per
+  pair instead of 25.5, reference roundings kept); in REFERENCED mode the plane-major flat detector set takes the
+  row-expansion loop.  Under torch.distributed the planes are split like ``array_split`` over the ranks (4 planes per
+  GPU at C5 on 8 GPUs) and all-gathered in place (SURVEY.md 8e);
 * ``psf_stack`` evaluates ``compute_psf_fft`` for a batch of planes with one batched ``torch.fft.fft2`` (a library
   call: north_star item 4 keeps the PSF out of the optimisation scope), plane p on rank p's ``array_split`` block.
 
@@ -24,7 +25,7 @@ import numpy as np
 
 from . import _lib
 from .psf import field_to_pupil
-from .wavecalc import PHASE_FAITHFUL, _any_device, fresnel_sum, fresnel_sum_sharded
+from .wavecalc import PHASE_FAITHFUL, _any_device, fresnel_sum_sharded
 
 __all__ = ["fresnel_sum_planes", "psf_stack", "compute_psf_fft_batch"]
 
@@ -40,13 +41,18 @@ def _dist_world():
 
 
 def fresnel_sum_planes(y, z, x_planes, u_back_x, u_back_y, u_back_z, u_back_u, k, ds=None, mode=PHASE_FAITHFUL,
-                       device=None):
+                       device=None, group=None):
     """Field of the back surface on the planes x = x_planes[p], all sampled at the same pixels (y[i], z[i]).
 
     y, z: float64[M] (a meshgrid-ordered focal grid: y fastest, like ``np.meshgrid(y_grid, z_grid)`` flattened,
     AKB_raytrace_20250312.py:13581-13589); x_planes: float64[P].  Returns complex128 (P, M): NumPy for NumPy inputs, a
-    torch CUDA tensor for device inputs.  With an initialised torch.distributed group of more than one rank the flat
-    (plane, pixel) index is sharded over the ranks and every rank returns the full stack."""
+    torch CUDA tensor for device inputs.
+
+    One ``akb_fresnel_sum_planes`` call: in the FAITHFUL / EXACT modes a thread owns one pixel on four planes (24 / 22.5
+    FP64 instructions per pair: the y and z terms of r^2 are shared by the four planes, the x term by the block); in
+    REFERENCED mode the plane-major flat detector set goes through the row-expansion loop.  With an initialised
+    torch.distributed NCCL group of more than one rank the PLANES are split like ``array_split`` over the ranks (fewer
+    planes than ranks: the flat (plane, pixel) index instead) and all-gathered: every rank returns the full stack."""
     import torch
     arrays = (y, z, u_back_x, u_back_y, u_back_z, u_back_u, ds)
     was_numpy = not _any_device(*arrays)
@@ -59,16 +65,43 @@ def fresnel_sum_planes(y, z, x_planes, u_back_x, u_back_y, u_back_z, u_back_u, k
     if yd.shape != zd.shape:
         raise ValueError("y and z must have the same length")
     xp = torch.as_tensor(np.ascontiguousarray(np.asarray(x_planes, dtype=np.float64).reshape(-1)), device=device) \
-        if not _lib.is_torch(x_planes) else x_planes.to(device=device, dtype=torch.float64).reshape(-1)
+        if not _lib.is_torch(x_planes) else x_planes.to(device=device, dtype=torch.float64).reshape(-1).contiguous()
     P, M = int(xp.shape[0]), int(yd.shape[0])
-    gx = xp.repeat_interleave(M)          # plane-major flat detector set: (p, i) -> p*M + i
-    gy, gz = yd.repeat(P), zd.repeat(P)
-    world, _ = _dist_world()
+    world, rank = _dist_world()
+    nccl = False
     if world > 1:
-        flat = fresnel_sum_sharded(gx, gy, gz, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, mode=mode, device=device)
-    else:
-        flat = fresnel_sum(gx, gy, gz, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, mode=mode, device=device)
-    out = flat.reshape(P, M)
+        import torch.distributed as dist
+        nccl = "nccl" in str(dist.get_backend(group))
+    if world > 1 and (P < world or not nccl):  # too few planes to give every rank one, or no NCCL: shard the flat index
+        gx = xp.repeat_interleave(M)           # plane-major flat detector set: (p, i) -> p*M + i
+        flat = fresnel_sum_sharded(gx, yd.repeat(P), zd.repeat(P), u_back_x, u_back_y, u_back_z, u_back_u, k, ds, mode=mode,
+                                   device=device, group=group)
+        out = flat.reshape(P, M)
+        return out.cpu().numpy() if was_numpy else out
+    sx, sy, sz = (_lib.dev_f64(a, device) for a in (u_back_x, u_back_y, u_back_z))
+    su = _lib.dev_c128(u_back_u, device)
+    if not (sx.shape == sy.shape == sz.shape == su.shape and sx.dim() == 1):
+        raise ValueError("u_back_x, u_back_y, u_back_z, u_back_u must be 1-D arrays of equal length")
+    sd = None
+    if ds is not None:
+        sd = _lib.dev_f64(ds, device)
+        if sd.numel() != sx.numel():
+            sd = sd.expand(sx.shape).contiguous()
+    out = torch.empty(P, M, dtype=torch.complex128, device=device)
+    b, c = _lib.shard_range(P, world, rank) if world > 1 else (0, P)
+    L = _lib.load()
+    with torch.cuda.device(device):
+        st = _lib.torch_stream_ptr(device)
+        if c > 0:
+            rc = L.akb_fresnel_sum_planes(_lib.dev_ptr(yd), _lib.dev_ptr(zd), M, _lib.dev_ptr(xp[b:b + c]), c, _lib.dev_ptr(sx),
+                                          _lib.dev_ptr(sy), _lib.dev_ptr(sz), _lib.dev_ptr(su),
+                                          _lib.dev_ptr(sd) if sd is not None else None, sx.shape[0], float(k),
+                                          _lib.dev_ptr(out[b:b + c]), int(mode), st)
+            _lib.check(rc, "akb_fresnel_sum_planes")
+        if world > 1:  # every plane is one item of 2*M doubles: in-place all-gather of the array_split blocks of planes
+            from .wavecalc import _nccl_comm
+            rc = L.akb_allgather_blocks(_nccl_comm(group, device), rank, world, _lib.dev_ptr(out), P, 2 * M, st)
+            _lib.check(rc, "akb_allgather_blocks")
     return out.cpu().numpy() if was_numpy else out
 
 

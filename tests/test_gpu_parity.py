@@ -663,19 +663,25 @@ def test_chain_opl_and_ray_wave_tail(akb, torch, golden):
 
 
 def test_through_focus_stack_and_batched_psf(akb, torch, golden):
-    """BASELINE config C5 as a product call (4 planes x 128x128 here): fresnel_sum_planes = one launch over the
-    plane-major flat detector set, every block on the planar-row loop; psf_stack = compute_psf_fft per plane with
-    one batched fft2 (vs the single-plane function, and vs the reference's psf_fft golden)."""
+    """BASELINE config C5 as a product call (6 planes x 128x128 here: one full group of four planes and a ragged one):
+    fresnel_sum_planes = one akb_fresnel_sum_planes launch, a thread owning one pixel on four planes; psf_stack =
+    compute_psf_fft per plane with one batched fft2 (vs the single-plane function, and vs the reference's golden)."""
     from akbraytracing_b200 import workloads
-    G, P = 128, 4
+    G, P = 128, 6
     w = workloads.traced_field_inputs("c3", 200, G, device="cuda")
     x0 = float(w["det_x"][0])
     planes = x0 + np.linspace(-1e-3, 1e-3, P)          # defocusForWave = 1e-3 (BIG:89)
-    _row_blocks(akb)
     stack = akb.fresnel_sum_planes(w["det_y"], w["det_z"], planes, w["src_x"], w["src_y"], w["src_z"], w["u"], w["k"], w["ds"])
     assert stack.shape == (P, G * G) and stack.is_cuda
-    assert _row_blocks(akb) > 0
     h = {k: v.cpu().numpy() for k, v in w.items() if k not in ("k", "trace")}
+    # the other two phase modes (EXACT: the four-plane kernel; REFERENCED: plane-major flat set, row expansion) and a
+    # pixel count that is not a multiple of the block size
+    for mode in (akb.PHASE_EXACT, akb.PHASE_REFERENCED):
+        other = akb.fresnel_sum_planes(w["det_y"][:5000], w["det_z"][:5000], planes[:5], w["src_x"], w["src_y"], w["src_z"],
+                                       w["u"], w["k"], w["ds"], mode=mode)
+        dev = float(torch.linalg.vector_norm(other - stack[:5, :5000]) / torch.linalg.vector_norm(stack[:5, :5000]))
+        print(f"through-focus mode {mode} vs faithful: rel-L2 {dev:.2e}")
+        assert other.shape == (5, 5000) and dev <= FIELD_TOL / 10
     rng = np.random.default_rng(9)
     for p in range(P):
         one = akb.fresnel_sum(torch.full_like(w["det_y"], planes[p]), w["det_y"], w["det_z"], w["src_x"], w["src_y"], w["src_z"],
