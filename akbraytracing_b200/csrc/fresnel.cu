@@ -935,8 +935,10 @@ KernelEntry make_entry(const char *name)
 // AKB_FRESNEL_VARIANT=<n> forces one (tools/variant_bench.py) and an index that does not exist is an error.
 constexpr int FORM_DEFAULT = FORM_TAN | FORM_POLAR | FORM_SHORTCOS | FORM_WFOLD;
 enum { V_DEFAULT = 0, V_DPT2 = 1, V_DPT1 = 2, V_REFERENCED = 3 };
-const KernelEntry *kernel_table(int *count)
+const KernelEntry *kernel_table(int *count_out)
 {
+    int dummy = 0;
+    int *count = count_out ? count_out : &dummy;
     static const KernelEntry entries[] = {
         // default: 25.5 FP64 instructions per pair on planar-row blocks (29 in the general loop), 2 x 256
         // threads per SM (measured in round 1: 3 blocks/SM at 80 registers spill, 1 block/SM starves the FP64
@@ -1111,13 +1113,21 @@ char *host_stage()
 
 namespace {
 
-// the through-focus kernel (FORM_PLANES): one pixel on four planes per thread; FAITHFUL and EXACT only
+#ifdef AKB_AB_VARIANTS
+// the through-focus kernel (FORM_PLANES): one pixel on four planes per thread; FAITHFUL and EXACT only.  24 instead of
+// 25.5 FP64 instructions per pair, and still 8 % SLOWER than the plane-major flat set through the planar-row loop
+// (568 vs 619 Gterms/s, profiles/r02_variants_ab.md section 7): ten row loads gate every loop iteration instead of seven
+// and queue behind the other warps' table look-ups (ncu: short_scoreboard 1.69 instead of 0.42 warps per issue cycle, FP64
+// pipe 74 % instead of 85 % active).  Kept as an A/B variant (AKB_PLANES_KERNEL=1 in an AKB_AB_VARIANTS build).
 const KernelEntry &planes_kernel()
 {
     static const KernelEntry e = make_entry<4, 256, 3, 4096, 2, FORM_DEFAULT | FORM_PLANES, 2, 256, BUILD_F | BUILD_E>(
         "dpt4 tile256x3 table4096 wfold, one pixel x four planes per thread");
     return e;
 }
+#else
+const KernelEntry &planes_kernel() { return *kernel_table(nullptr); } // never launched in product builds (planes == 0 always)
+#endif
 
 // planes == 0: det_x/y/z are M detector points.  planes > 0 (akb_fresnel_sum_planes): det_x holds the `planes` plane
 // positions, det_y/z the M pixels of one plane, out is [planes][M].
@@ -1253,10 +1263,13 @@ extern "C" int akb_fresnel_sum_planes(const double *det_y, const double *det_z, 
     AKB_REQUIRE(planes >= 0 && M >= 0, "planes and M must be non-negative");
     if (planes == 0 || M == 0) return AKB_OK;
     AKB_REQUIRE(x_planes && det_y && det_z && out, "detector/out pointers must not be NULL");
-    if (mode != AKB_PHASE_REFERENCED)
+#ifdef AKB_AB_VARIANTS
+    if (mode != AKB_PHASE_REFERENCED && getenv("AKB_PLANES_KERNEL"))
         return fresnel_sum_impl(x_planes, det_y, det_z, M, planes, src_x, src_y, src_z, src_u, src_ds, N, k, out, mode, stream);
-    // REFERENCED: the plane-major flat detector set; every 1024-point block lies in one row of one plane and takes the
-    // row-expansion loop, the fastest one there is
+#endif
+    // The plane-major flat detector set: every 1024-point block lies in one row of one plane and takes the planar-row
+    // loop (REFERENCED: with the row expansion).  A kernel in which a thread keeps one pixel for four planes was built and
+    // measured slower (see planes_kernel above).
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long total = (long long)M * planes;
     double *flat = nullptr;

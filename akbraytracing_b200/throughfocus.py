@@ -5,11 +5,12 @@ The reference computes one plane per run of the Wavecalc script (focal grid and 
 Wavecalc_raytrace_fromData_CPU0402.py:330-370) and one PSF per call of ``compute_psf_fft`` (psf_fft.py:29-125, fed by
 ``psf_calc``, AKB_raytrace_20250312.py:1121-1200 with ``pad_factor=16``).  Here
 
-* ``fresnel_sum_planes`` is one ``akb_fresnel_sum_planes`` launch: a thread keeps one (y, z) pixel for four planes, so
-  the y and z terms of r^2 are shared by four pairs and the x term by the whole block (24 FP64 instructions per
-  pair instead of 25.5, reference roundings kept); in REFERENCED mode the plane-major flat detector set takes the
-  row-expansion loop.  Under torch.distributed the planes are split like ``array_split`` over the ranks (4 planes per
-  GPU at C5 on 8 GPUs) and all-gathered in place (SURVEY.md 8e);
+* ``fresnel_sum_planes`` is one ``akb_fresnel_sum_planes`` launch over the plane-major flat detector set: every
+  1024-point block of the pair kernel lies in one row of one plane and takes the planar-row loop (REFERENCED mode: with
+  the row expansion).  Under torch.distributed the planes are split like ``array_split`` over the ranks (4 planes per
+  GPU at C5 on 8 GPUs) and all-gathered in place.  (A kernel in which a thread keeps one pixel for
+  four planes -- y and z terms of r^2 shared by four pairs, 24 instead of 25.5 FP64 instructions per pair -- was built
+  and measured 8 % slower: its ten row loads per loop iteration stall on shared memory)
 * ``psf_stack`` evaluates ``compute_psf_fft`` for a batch of planes with one batched ``torch.fft.fft2`` (a library
   call: north_star item 4 keeps the PSF out of the optimisation scope), plane p on rank p's ``array_split`` block.
 
@@ -48,9 +49,8 @@ def fresnel_sum_planes(y, z, x_planes, u_back_x, u_back_y, u_back_z, u_back_u, k
     AKB_raytrace_20250312.py:13581-13589); x_planes: float64[P].  Returns complex128 (P, M): NumPy for NumPy inputs, a
     torch CUDA tensor for device inputs.
 
-    One ``akb_fresnel_sum_planes`` call: in the FAITHFUL / EXACT modes a thread owns one pixel on four planes (24 / 22.5
-    FP64 instructions per pair: the y and z terms of r^2 are shared by the four planes, the x term by the block); in
-    REFERENCED mode the plane-major flat detector set goes through the row-expansion loop.  With an initialised
+    One ``akb_fresnel_sum_planes`` call (the plane-major flat detector set through the planar-row loop; REFERENCED mode:
+    with the row expansion).  With an initialised
     torch.distributed NCCL group of more than one rank the PLANES are split like ``array_split`` over the ranks (fewer
     planes than ranks: the flat (plane, pixel) index instead) and all-gathered: every rank returns the full stack."""
     import torch

@@ -95,10 +95,10 @@ int akb_fresnel_sum_host(const double *det_x, const double *det_y, const double 
 
 /* Through-focus stack (BASELINE config 5; the reference computes one plane per run of the Wavecalc script,
  * CPU0402:330-370): the field of one source surface on `planes` detector planes x = x_planes[p] that share the pixels
- * (det_y[i], det_z[i]), i < M.  out = complex128[planes][M].  FAITHFUL / EXACT: a thread owns one pixel on four planes, so
- * (y - Y)^2 and (z - Z)^2 are shared by four pairs and (x_p - X)^2 by the whole block: 24 instead of 25.5 FP64
- * instructions per pair, same operations in the same order as akb_fresnel_sum plane by plane.  REFERENCED: evaluated as the
- * plane-major flat detector set (row expansion).  x_planes is a DEVICE pointer like the other arrays. */
+ * (det_y[i], det_z[i]), i < M.  out = complex128[planes][M].  One launch over the plane-major flat detector set: with
+ * meshgrid-ordered pixels every block lies in one row of one plane and takes the planar-row loop (REFERENCED: with the row
+ * expansion), bit-identical to akb_fresnel_sum plane by plane up to the order of the partial sums.  x_planes is a DEVICE
+ * pointer like the other arrays. */
 int akb_fresnel_sum_planes(const double *det_y, const double *det_z, int64_t M, const double *x_planes, int planes,
                            const double *src_x, const double *src_y, const double *src_z, const double *src_u,
                            const double *src_ds, int64_t N, double k, double *out, int mode, void *stream);
