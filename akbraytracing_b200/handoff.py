@@ -36,7 +36,7 @@ def calc_dS(points, ray_num_V, ray_num_H):
     with torch.cuda.device(dev):
         rc = _lib.load().akb_calc_ds(_lib.dev_ptr(p), nV, nH, _lib.dev_ptr(out), _lib.torch_stream_ptr(dev))
     _lib.check(rc, "akb_calc_ds")
-    return out.cpu().numpy() if numpy_io else out
+    return _lib.to_host(out) if numpy_io else out
 
 
 def opl_to_field(opl, k, amp=None):
@@ -51,4 +51,4 @@ def opl_to_field(opl, k, amp=None):
         rc = _lib.load().akb_opl_to_field(_lib.dev_ptr(o), _lib.dev_ptr(a) if a is not None else None, o.shape[0],
                                           float(k), _lib.dev_ptr(out), _lib.torch_stream_ptr(dev))
     _lib.check(rc, "akb_opl_to_field")
-    return out.cpu().numpy() if numpy_io else out
+    return _lib.to_host(out) if numpy_io else out

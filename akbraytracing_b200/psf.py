@@ -72,8 +72,8 @@ def compute_psf_fft(opd_m, amp, wavelength_m, pupil_dx_m, focal_length_m, pad_fa
         inten = inten / peak
     ef = U_im / np.sqrt(peak if peak > 0 else 1.0) if return_efield else None
     if numpy_io:
-        inten = inten.cpu().numpy()
-        ef = ef.cpu().numpy() if ef is not None else None
+        inten = _lib.to_host(inten)
+        ef = _lib.to_host(ef) if ef is not None else None
     else:
         x_im, y_im = torch.as_tensor(x_im, device=dev), torch.as_tensor(y_im, device=dev)
     if return_efield:

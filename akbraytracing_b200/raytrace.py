@@ -90,7 +90,7 @@ class _Ctx:
         return [int(v) for v in self.flags.cpu().tolist()]  # synchronises the stream
 
     def out(self, t):
-        return t.cpu().numpy() if self.numpy_io else t
+        return _lib.to_host(t) if self.numpy_io else t
 
     def nan_like(self, t):
         return self.out(self.torch.full_like(t, float("nan")))

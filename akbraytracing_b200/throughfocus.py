@@ -77,7 +77,7 @@ def fresnel_sum_planes(y, z, x_planes, u_back_x, u_back_y, u_back_z, u_back_u, k
         flat = fresnel_sum_sharded(gx, yd.repeat(P), zd.repeat(P), u_back_x, u_back_y, u_back_z, u_back_u, k, ds, mode=mode,
                                    device=device, group=group)
         out = flat.reshape(P, M)
-        return out.cpu().numpy() if was_numpy else out
+        return _lib.to_host(out) if was_numpy else out
     sx, sy, sz = (_lib.dev_f64(a, device) for a in (u_back_x, u_back_y, u_back_z))
     su = _lib.dev_c128(u_back_u, device)
     if not (sx.shape == sy.shape == sz.shape == su.shape and sx.dim() == 1):
@@ -102,7 +102,7 @@ def fresnel_sum_planes(y, z, x_planes, u_back_x, u_back_y, u_back_z, u_back_u, k
             from .wavecalc import _nccl_comm
             rc = L.akb_allgather_blocks(_nccl_comm(group, device), rank, world, _lib.dev_ptr(out), P, 2 * M, st)
             _lib.check(rc, "akb_allgather_blocks")
-    return out.cpu().numpy() if was_numpy else out
+    return _lib.to_host(out) if was_numpy else out
 
 
 def compute_psf_fft_batch(opd_m, amp, wavelength_m, pupil_dx_m, focal_length_m, pad_factor=2, window=None,
@@ -151,8 +151,8 @@ def compute_psf_fft_batch(opd_m, amp, wavelength_m, pupil_dx_m, focal_length_m, 
     inten = inten / safe
     ef = U_im / torch.sqrt(safe) if return_efield else None
     if numpy_io:
-        inten = inten.cpu().numpy()
-        ef = ef.cpu().numpy() if ef is not None else None
+        inten = _lib.to_host(inten)
+        ef = _lib.to_host(ef) if ef is not None else None
     else:
         x_im, y_im = torch.as_tensor(x_im, device=dev), torch.as_tensor(y_im, device=dev)
     return (inten, x_im, y_im, ef) if return_efield else (inten, x_im, y_im)
@@ -195,6 +195,6 @@ def psf_stack(fields, grid_shape, wavelength_m, pupil_dx_m, focal_length_m, pad_
     else:
         I = torch.empty(0, py, px, dtype=torch.float64, device=f.device)
     if numpy_io:
-        return dict(planes=mine, I=I.cpu().numpy(), x=None if x_im is None else x_im.cpu().numpy(),
-                    y=None if y_im is None else y_im.cpu().numpy())
+        return dict(planes=mine, I=_lib.to_host(I), x=None if x_im is None else _lib.to_host(x_im),
+                    y=None if y_im is None else _lib.to_host(y_im))
     return dict(planes=mine, I=I, x=x_im, y=y_im)

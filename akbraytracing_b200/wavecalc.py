@@ -17,6 +17,7 @@ CuPy's default, so a CuPy caller's pending kernels are ordered before ours.  The
 """
 from __future__ import annotations
 
+import ctypes
 import os
 import time
 
@@ -224,7 +225,16 @@ def fresnel_sum_sharded(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds=N
         def compute_local(xs, ys, zs, *r):
             return fresnel_sum(xs, ys, zs, *r, mode=mode, device=device)
         out = _sharded_over_group(compute_local, x, y, z, rest, group, gather)
-        return out.cpu().numpy() if (was_numpy and _lib.is_torch(out)) else out
+        return _lib.to_host(out) if (was_numpy and _lib.is_torch(out)) else out
+    begin = 0
+    if not _any_device(x, y, z):
+        # host detector arrays: only this rank's block crosses PCIe (1/world of the coordinates); the entry point
+        # indexes det[begin + i], so it gets the block's address moved back by `begin` elements
+        x, y, z = (_lib.as_f64(a) for a in (x, y, z))
+        if not (x.shape == y.shape == z.shape and x.ndim == 1):
+            raise ValueError("x, y, z must be 1-D arrays of equal length")
+        begin, count = _lib.shard_range(total, world, rank)
+        x, y, z = (a[begin:begin + count] for a in (x, y, z))
     dx, dy, dz = (_lib.dev_f64(a, device) for a in (x, y, z))
     sx, sy, sz = (_lib.dev_f64(a, device) for a in (u_back_x, u_back_y, u_back_z))
     su = _lib.dev_c128(u_back_u, device)
@@ -244,12 +254,11 @@ def fresnel_sum_sharded(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds=N
     comm = _nccl_comm(group, device)
     with torch.cuda.device(device):
         rc = _lib.load().akb_fresnel_sum_sharded(
-            comm, rank, world, _lib.dev_ptr(dx), _lib.dev_ptr(dy), _lib.dev_ptr(dz), total,
-            _lib.dev_ptr(sx), _lib.dev_ptr(sy), _lib.dev_ptr(sz), _lib.dev_ptr(su),
+            comm, rank, world, *(ctypes.c_void_p(t.data_ptr() - 8 * begin) for t in (dx, dy, dz)), total, _lib.dev_ptr(sx), _lib.dev_ptr(sy), _lib.dev_ptr(sz), _lib.dev_ptr(su),
             _lib.dev_ptr(sd) if sd is not None else None, sx.shape[0], float(k), _lib.dev_ptr(out), int(mode),
             1 if broadcast_sources else 0, _lib.torch_stream_ptr(device))
     _lib.check(rc, "akb_fresnel_sum_sharded")
-    return out.cpu().numpy() if was_numpy else out
+    return _lib.to_host(out) if was_numpy else out
 
 
 def forward_propagation_cupy_batch_multi_gpu(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, devices=None,
@@ -283,7 +292,7 @@ def forward_propagation_cupy_batch_multi_gpu(x, y, z, u_back_x, u_back_y, u_back
         parts.append(_fresnel_device(x[sl], y[sl], z[sl], u_back_x, u_back_y, u_back_z, u_back_u, k, ds, mode, dev))
     out = torch.cat([p.to(home, non_blocking=True) for p in parts])
     if was_numpy:
-        return out.cpu().numpy()
+        return _lib.to_host(out)
     return out
 
 

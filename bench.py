@@ -367,7 +367,10 @@ def run_ours(args):
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        return terms_step * steps / float(dt.item()), res, sum(a.nbytes for a in host)
+        # bytes that cross PCIe on ALL ranks: every rank uploads the whole source set and its own block of the
+        # detector coordinates (fresnel_sum_sharded slices host arrays before the upload)
+        moved = world * sum(a.nbytes for a in host[3:]) + sum(a.nbytes for a in host[:3])
+        return terms_step * steps / float(dt.item()), res, moved
     e2e_steps = max(1, min(args.steps, 10))
     e2e_value, host_out, h2d = e2e_run(True, e2e_steps)
     e2e_pageable, _, _ = e2e_run(False, max(1, min(args.steps, 5)))
@@ -411,7 +414,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world), "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": "terms/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+            "e2e": {"value": e2e_value, "unit": "terms/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h * world,
                     "api": ("forward_propagation_cupy_batch_multi_gpu with NumPy buffers (one device: akb_fresnel_sum_host, "
                             "H2D + kernels + D2H)" if world == 1 else
                             "forward_propagation_cupy_batch_multi_gpu with NumPy buffers on every rank "
