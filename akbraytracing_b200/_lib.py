@@ -168,7 +168,10 @@ def to_host(t):
     nbytes = t.numel() * t.element_size()
     if not t.is_cuda or nbytes < (1 << 20) or nbytes > (1 << 30):
         return t.detach().cpu().numpy()
-    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    try:
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    except RuntimeError:  # no page-locked memory to be had (RLIMIT_MEMLOCK, container limits): an ordinary array
+        return t.detach().cpu().numpy()
     host.copy_(t.detach())
     return host.numpy()
 
