@@ -383,7 +383,10 @@ __device__ __forceinline__ PairA pair_phase_a_from_s(double s, const PhaseConst 
 {
     PairA a;
     double root;
-    sqrt_and_half_rinv(s, root, a.h);
+    if (MODE == AKB_PHASE_FAITHFUL)
+        sqrt_and_half_rinv(s, root, a.h); // correctly rounded, like np.sqrt (CPU0402:80)
+    else
+        sqrt_and_half_rinv_g2(s, root, a.h);
     if (MODE == AKB_PHASE_FAITHFUL) {
         a.p = mul(pc.k, root); // CPU0402:82: |phase| = fl(k*dist)
         a.t = fma_(a.p, pc.inv_u, magic);
