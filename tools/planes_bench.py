@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Through-focus stack on one GPU: akb_fresnel_sum_planes (one pixel on four planes per thread) against the same stack
-evaluated as a plane-major flat detector set by akb_fresnel_sum, per phase mode.  Usage: planes_bench.py [G] [P]"""
+"""Through-focus stack on one GPU: akb_fresnel_sum_planes against the same stack evaluated as a plane-major flat detector
+set by akb_fresnel_sum, per phase mode.  In a product build the two are the same kernel; in an AKB_AB_VARIANTS build
+with AKB_PLANES_KERNEL=1 the first one runs the rejected "one pixel on four planes per thread" kernel
+(profiles/r02_variants_ab.md section 7).  Usage: planes_bench.py [G] [P]"""
 import ctypes
 import os
 import sys

@@ -1,5 +1,9 @@
+#!/usr/bin/env python
+"""ncu driver for the A/B of profiles/r02_variants_ab.md section 7: one through-focus stack through
+akb_fresnel_sum_planes and the same stack as a flat detector set (AKB_AB_VARIANTS build + AKB_PLANES_KERNEL=1 to reach
+the four-plane kernel)."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import akbraytracing_b200 as akb
 from akbraytracing_b200 import workloads
