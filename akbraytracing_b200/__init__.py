@@ -2,7 +2,8 @@
 Kakekakechan/AKBRaytracing: the Huygens-Fresnel pair sum (wavecalc) and the ray / quadric-mirror
 chain (raytrace).  Hand-written CUDA behind a C-ABI (include/akb_b200.h); no CPU fallback."""
 from . import _lib
-from .wavecalc import (PHASE_EXACT, PHASE_FAITHFUL, PHASE_REFERENCED, WaveField3D, forward_propagation_cupy_batch,
+from .wavecalc import (PHASE_EXACT, PHASE_FAITHFUL, PHASE_REFERENCED, WaveField3D, compute_u, compute_u_parallel,
+                       forward_propagation_cupy_batch,
                        forward_propagation_cupy_batch_multi_gpu, forward_propagation_numpy_batch,
                        fresnel_sum, fresnel_sum_sharded)
 from .raytrace import (PlanePoints, ell, intersect_reflect, mirr_ray_intersection, norm_vector,

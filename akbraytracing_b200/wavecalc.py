@@ -102,6 +102,18 @@ def fresnel_sum(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds=None, mod
     return _fresnel_host(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, mode, -1 if device is None else device)
 
 
+def compute_u_parallel(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k):
+    """Drop-in for the numba kernel CPU0402:71-85: the pair sum with the weights as given (no ``ds``)."""
+    return fresnel_sum(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k)
+
+
+def compute_u(i, x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k):
+    """Drop-in for CPU0402:54-63: the field at detector point ``i`` alone (a complex scalar for NumPy input)."""
+    u = fresnel_sum(x[i:i + 1] if i != -1 else x[-1:], y[i:i + 1] if i != -1 else y[-1:],
+                    z[i:i + 1] if i != -1 else z[-1:], u_back_x, u_back_y, u_back_z, u_back_u, k)
+    return u[0]
+
+
 def forward_propagation_numpy_batch(x, y, z, u_back_x, u_back_y, u_back_z, u_back_u, k, ds, num_cores=None):
     """Drop-in for CPU0402:87-124.  ``num_cores`` is accepted and ignored (it is ineffective in
     the reference too: the env var is written after numba is imported, CPU0402:105-107)."""

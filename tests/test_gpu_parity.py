@@ -65,6 +65,18 @@ def test_fresnel_device_abi_matches_reference_golden(akb, torch, golden, name):
     assert rel_l2(got.cpu().numpy(), c["ref"]) <= 1e-12
 
 
+def test_compute_u_names_match_reference_golden(akb, golden):
+    """compute_u_parallel (CPU0402:71-85) and compute_u (CPU0402:54-63): weights as given, no ds."""
+    c = golden("fresnel_ref").group("patch_euv")
+    w = c["u"] * c["ds"]
+    got = akb.compute_u_parallel(c["x"], c["y"], c["z"], c["sx"], c["sy"], c["sz"], w, float(c["k"]))
+    assert isinstance(got, np.ndarray) and got.shape == c["ref"].shape
+    assert rel_l2(got, c["ref"]) <= 1e-12 and rel_l2(got, c["ref_numpy"]) <= 1e-12
+    for i in (0, 3, len(c["x"]) - 1, -1):
+        one = akb.compute_u(i, c["x"], c["y"], c["z"], c["sx"], c["sy"], c["sz"], w, float(c["k"]))
+        assert np.ndim(one) == 0 and abs(one - c["ref_numpy"][i]) <= 1e-12 * abs(c["ref_numpy"][i])
+
+
 def test_fresnel_coincident_point_is_nan_like_reference(akb, golden):
     c = golden("fresnel_ref").group("coincident")
     got = akb.forward_propagation_numpy_batch(c["x"], c["y"], c["z"], c["sx"], c["sy"], c["sz"], c["u"],
