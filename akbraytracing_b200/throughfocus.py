@@ -10,7 +10,7 @@ Wavecalc_raytrace_fromData_CPU0402.py:330-370) and one PSF per call of ``compute
   the row expansion).  Under torch.distributed the planes are split like ``array_split`` over the ranks (4 planes per
   GPU at C5 on 8 GPUs) and all-gathered in place.  (A kernel in which a thread keeps one pixel for
   four planes -- y and z terms of r^2 shared by four pairs, 24 instead of 25.5 FP64 instructions per pair -- was built
-  and measured 8 % slower: its ten row loads per loop iteration stall on shared memory; DESIGN.md section 4.)
+  and measured 8 % slower: its ten row loads per loop iteration stall on shared memory; DESIGN.md section 9.)
 * ``psf_stack`` evaluates ``compute_psf_fft`` for a batch of planes with one batched ``torch.fft.fft2`` (a library
   call: north_star item 4 keeps the PSF out of the optimisation scope), plane p on rank p's ``array_split`` block.
 
