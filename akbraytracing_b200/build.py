@@ -55,6 +55,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
         cmd = [nvcc, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
+        if src == "fresnel.cu" and os.environ.get("AKB_FRESNEL_PTXAS"):  # A/B of ptxas options on the pair kernels
+            cmd[1:1] = [f"-Xptxas={o}" for o in os.environ["AKB_FRESNEL_PTXAS"].split()]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
