@@ -91,3 +91,15 @@ def test_handoff_downsampling_is_every_second_sample():
     assert (sv, sh) == (nV, 7) and np.array_equal(out, g[:, :, ::2].reshape(3, -1))
     out, sv, sh = _downsample(cloud, nV, nH, 4, 2)
     assert (sv, sh) == (5, 4) and np.array_equal(out, g[:, ::2, ::4].reshape(3, -1))
+
+
+def test_to_host_of_a_cpu_tensor_is_a_plain_array():
+    """_lib.to_host: page-locked staging is for CUDA tensors only; anything else converts like .cpu().numpy()."""
+    import torch
+    from akbraytracing_b200 import _lib
+    t = torch.arange(6, dtype=torch.float64).reshape(2, 3).requires_grad_(False)
+    a = _lib.to_host(t)
+    assert isinstance(a, np.ndarray) and a.shape == (2, 3) and a.dtype == np.float64
+    assert np.array_equal(a, np.arange(6.0).reshape(2, 3))
+    c = _lib.to_host(torch.ones(4, dtype=torch.complex128))
+    assert c.dtype == np.complex128 and c.sum() == 4
